@@ -1,0 +1,837 @@
+// relem_api.cu -- implementation of the C ABI declared in include/relem.h.
+//
+// Built by nvcc for sm_100a into rnaelem_b200/librelem.so (the product).  The same file builds, with
+// -DRELEM_HOST_EMU under g++, into tests/emu/librelem_emu.so: a single-threaded host emulation of the kernel
+// source used only to debug the DP logic in a container without a GPU.  The product library contains no host
+// implementation of the DP and fails loudly (relem_create -> RELEM_ECUDA) when no GPU is usable.
+#include "../../include/relem.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <numeric>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "dp_layout.hpp"
+#include "host_model.hpp"
+
+#ifndef RELEM_HOST_EMU
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#endif
+
+using namespace relem;
+using namespace relem::dp;
+
+namespace {
+
+std::string g_create_error;
+
+// ---------------------------------------------------------------------------------- device abstraction
+#ifdef RELEM_HOST_EMU
+struct Dev {
+  static bool alloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p != nullptr; }
+  static void free(void* p) { std::free(p); }
+  static bool h2d(void* d, const void* h, size_t n) { if (n) std::memcpy(d, h, n); return true; }
+  static bool d2h(void* h, const void* d, size_t n) { if (n) std::memcpy(h, d, n); return true; }
+  static bool zero(void* d, size_t n) { if (n) std::memset(d, 0, n); return true; }
+};
+#else
+struct Dev {
+  static bool alloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) == cudaSuccess; }
+  static void free(void* p) { cudaFree(p); }
+  static bool h2d(void* d, const void* h, size_t n) { return !n || cudaMemcpy(d, h, n, cudaMemcpyHostToDevice) == cudaSuccess; }
+  static bool d2h(void* h, const void* d, size_t n) { return !n || cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost) == cudaSuccess; }
+  static bool zero(void* d, size_t n) { return !n || cudaMemset(d, 0, n) == cudaSuccess; }
+};
+#endif
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  bool reserve(size_t n) {
+    if (n <= bytes && p) return true;
+    if (p) Dev::free(p);
+    p = nullptr; bytes = 0;
+    if (!Dev::alloc(&p, n)) { p = nullptr; return false; }
+    bytes = n;
+    return true;
+  }
+  void release() { if (p) Dev::free(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+template <class T> bool upload(DevBuf& b, const std::vector<T>& v) {
+  if (!b.reserve(v.size() * sizeof(T))) return false;
+  return Dev::h2d(b.p, v.data(), v.size() * sizeof(T));
+}
+
+struct TimingEntry { const char* name; float ms; int launches; };
+
+}  // namespace
+
+struct relem_batch {
+  int nseq = 0;
+  int Lmax = 0;
+  long long total_len = 0;
+  std::vector<long long> off;
+  std::vector<unsigned char> kind;
+  std::vector<int> gate;
+  bool has_gate = false;
+  DevBuf d_seq, d_off, d_ws, d_kind, d_gate, d_order;
+  long long cells = 0;
+};
+
+struct relem_ctx {
+  int dev = 0;
+  std::string err;
+  bool have_energy = false, have_pattern = false, have_params = false;
+  EnergyTables et;
+  int max_span = 0, max_iloop = 0, no_ene = 0;
+  double min_bpp = 0;
+  ProfileHMM hmm;
+  FlatHMM flat, nullflat;
+  int no_rss = 0, no_prf = 0;
+  int n_theta = 0;
+  DevBuf d_energy, d_codes, d_hmm, d_null, d_n2s, d_theta, d_null_theta;
+  DevBuf d_scratch, d_queue, d_res, d_Z, d_ENo, d_ENx, d_EH, d_eff, d_skip;
+  DevBuf d_s1, d_s2, d_s3, d_s4, d_s5, d_s6, d_s7, d_s8, d_s9, d_s10;
+  DevEnergy den;
+  DevHMM dh, dnull;
+  DevParams dpar, dnullpar;
+  std::vector<TimingEntry> timing;
+#ifndef RELEM_HOST_EMU
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  void* nccl_lib = nullptr;
+  void* nccl_comm = nullptr;
+  DevBuf d_coll;
+#endif
+};
+
+namespace {
+
+int fail(relem_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#ifndef RELEM_HOST_EMU
+#define CUDA_TRY(c, expr)                                                                        \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return fail(c, RELEM_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+#endif
+
+int code_of(const std::string& s, int len) {
+  if ((int)s.size() != len) return -1;
+  int c = 0;
+  for (char ch : s) {
+    int b;
+    switch (ch) {
+      case 'N': b = 0; break; case 'A': b = 1; break; case 'C': b = 2; break; case 'G': b = 3; break;
+      case 'U': b = 4; break; default: return -1;
+    }
+    c = c * 5 + b;
+  }
+  return c;
+}
+
+const int kMaxHairpin = 10002;
+
+bool upload_energy(relem_ctx* c) {
+  const EnergyTables& t = c->et;
+  std::vector<double> blob;
+  auto put = [&](const double* p, size_t n) { size_t o = blob.size(); blob.insert(blob.end(), p, p + n); return o; };
+  int HL = std::min(c->max_span, kMaxHairpin - 2) + 2;
+  std::vector<double> hl(HL);
+  for (int d = 0; d < HL; ++d) hl[d] = t.hairpin_len(d);
+  size_t o_hl = put(hl.data(), HL);
+  size_t o_mmh = put(&t.mismatch_h[0][0][0], 175), o_mmi = put(&t.mismatch_i[0][0][0], 175);
+  size_t o_mmm = put(&t.mismatch_m[0][0][0], 200), o_1ni = put(&t.mismatch_1ni[0][0][0], 175);
+  size_t o_23i = put(&t.mismatch_23i[0][0][0], 175), o_ext = put(&t.mismatch_ext[0][0][0], 200);
+  size_t o_st = put(&t.stack[0][0], 49), o_bu = put(t.bulge, 31), o_in = put(t.internal, 31), o_ni = put(t.ninio, 31);
+  size_t o_d5 = put(&t.dangle5[0][0], 40), o_d3 = put(&t.dangle3[0][0], 40);
+  size_t o_11 = put(&t.int11[0][0][0][0], 1600), o_21 = put(&t.int21[0][0][0][0][0], 8000);
+  size_t o_22 = put(&t.int22[0][0][0][0][0][0], 40000);
+  std::vector<int> codes;
+  std::vector<double> w3, w4, w6;
+  std::vector<int> c3, c4, c6;
+  // entries keep their list position (first match wins); malformed entries can never match a window
+  for (size_t k = 0; k < t.tri.size(); ++k) { c3.push_back(code_of(t.tri[k], 5)); w3.push_back(t.tri_w[k]); }
+  for (size_t k = 0; k < t.tetra.size(); ++k) { c4.push_back(code_of(t.tetra[k], 6)); w4.push_back(t.tetra_w[k]); }
+  for (size_t k = 0; k < t.hexa.size(); ++k) { c6.push_back(code_of(t.hexa[k], 8)); w6.push_back(t.hexa_w[k]); }
+  double dummy = 0;
+  size_t o_w3 = put(w3.empty() ? &dummy : w3.data(), std::max<size_t>(1, w3.size()));
+  size_t o_w4 = put(w4.empty() ? &dummy : w4.data(), std::max<size_t>(1, w4.size()));
+  size_t o_w6 = put(w6.empty() ? &dummy : w6.data(), std::max<size_t>(1, w6.size()));
+  size_t oc3 = codes.size(); codes.insert(codes.end(), c3.begin(), c3.end()); codes.push_back(-2);
+  size_t oc4 = codes.size(); codes.insert(codes.end(), c4.begin(), c4.end()); codes.push_back(-2);
+  size_t oc6 = codes.size(); codes.insert(codes.end(), c6.begin(), c6.end()); codes.push_back(-2);
+  if (!upload(c->d_energy, blob) || !upload(c->d_codes, codes)) return false;
+  const double* b = c->d_energy.as<double>();
+  const int* ic = c->d_codes.as<int>();
+  DevEnergy& e = c->den;
+  e.hairpin_len = b + o_hl; e.mismatch_h = b + o_mmh; e.mismatch_i = b + o_mmi; e.mismatch_m = b + o_mmm;
+  e.mismatch_1ni = b + o_1ni; e.mismatch_23i = b + o_23i; e.mismatch_ext = b + o_ext; e.stack = b + o_st;
+  e.bulge = b + o_bu; e.internal = b + o_in; e.ninio = b + o_ni; e.dangle5 = b + o_d5; e.dangle3 = b + o_d3;
+  e.int11 = b + o_11; e.int21 = b + o_21; e.int22 = b + o_22;
+  e.term_au = t.term_au; e.mlintern = t.mlintern; e.mlclosing = t.mlclosing;
+  e.tri_code = ic + oc3; e.tri_w = b + o_w3; e.ntri = (int)c3.size();
+  e.tetra_code = ic + oc4; e.tetra_w = b + o_w4; e.ntetra = (int)c4.size();
+  e.hexa_code = ic + oc6; e.hexa_w = b + o_w6; e.nhexa = (int)c6.size();
+  e.no_ene = c->no_ene; e.max_span = c->max_span; e.max_iloop = c->max_iloop;
+  e.filter = c->min_bpp != 0. ? 1 : 0;
+  e.min_lnbpp = std::log(c->min_bpp);
+  return true;
+}
+
+bool upload_hmm(const FlatHMM& f, DevBuf& buf, DevHMM& d) {
+  std::vector<int> blob;
+  auto put = [&](const std::vector<int>& v) { size_t o = blob.size(); blob.insert(blob.end(), v.begin(), v.end()); blob.push_back(0); return o; };
+  size_t o1 = put(f.st_l), o2 = put(f.st_r), o3 = put(f.is_loop), o4 = put(f.right_off), o5 = put(f.right_idx),
+         o6 = put(f.left_off), o7 = put(f.left_idx), o8 = put(f.pair_off), o9 = put(f.pair_idx), o10 = put(f.quad_off),
+         o11 = put(f.quad_s1), o12 = put(f.quad_s2), o13 = put(f.quad_s3), o14 = put(f.split_off),
+         o15 = put(f.split_left), o16 = put(f.split_right), o17 = put(f.node), o18 = put(f.theta_id),
+         o19 = put(f.theta_off);
+  if (!upload(buf, blob)) return false;
+  const int* b = buf.as<int>();
+  d.M = f.M; d.S = f.S;
+  d.st_l = b + o1; d.st_r = b + o2; d.is_loop = b + o3; d.right_off = b + o4; d.right_idx = b + o5;
+  d.left_off = b + o6; d.left_idx = b + o7; d.pair_off = b + o8; d.pair_idx = b + o9; d.quad_off = b + o10;
+  d.quad_s1 = b + o11; d.quad_s2 = b + o12; d.quad_s3 = b + o13; d.split_off = b + o14; d.split_left = b + o15;
+  d.split_right = b + o16; d.node = b + o17; d.theta_id = b + o18; d.theta_off = b + o19;
+  d.s00 = f.s00; d.s0M2 = f.s0M2; d.s0M1 = f.s0M1;
+  return true;
+}
+
+struct Launch {
+  relem_ctx* c;
+  SlotLayout lay;
+  int nslots = 0;
+};
+
+// choose the number of resident CTAs (= scratch slots) and make sure the scratch fits
+int plan_launch(relem_ctx* c, const relem_batch* b, int nch, bool coupled, const void* kernel, Launch& L) {
+  int S = c->flat.S, M = c->flat.M;
+  L.c = c;
+  L.lay = make_layout(std::max(1, b->Lmax), c->max_span, S, M, c->n_theta, nch, coupled);
+  unsigned long long band = (unsigned long long)NPLANE * (b->Lmax + 1) * (L.lay.Wmax + 1) * (coupled ? S : 1);
+  if (band >= (1ull << 31)) return fail(c, RELEM_EINVAL, "band table of one sequence exceeds 2^31 entries");
+#ifdef RELEM_HOST_EMU
+  (void)kernel;
+  L.nslots = 1;
+#else
+  if (L.lay.sm_total > 227 * 1024) return fail(c, RELEM_EINVAL, "sequence too long: masks do not fit shared memory");
+  CUDA_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.lay.sm_total));
+  int occ = 0;
+  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, L.lay.sm_total));
+  if (occ < 1) return fail(c, RELEM_ECUDA, "kernel cannot be resident (occupancy 0)");
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
+  size_t avail = free_b + c->d_scratch.bytes;
+  size_t per = L.lay.stride * sizeof(double);
+  long long by_mem = (long long)((avail * 0.85) / (double)per);
+  L.nslots = (int)std::min<long long>(std::min<long long>(b->nseq, (long long)c->sm_count * occ), by_mem);
+  if (const char* e = std::getenv("RELEM_MAX_SLOTS")) L.nslots = std::min(L.nslots, std::max(1, std::atoi(e)));
+  if (L.nslots < 1) return fail(c, RELEM_ENOMEM, "not enough device memory for one sequence slot");
+#endif
+  if (!c->d_scratch.reserve((size_t)L.nslots * L.lay.stride * sizeof(double)))
+    return fail(c, RELEM_ENOMEM, "scratch allocation failed");
+  if (!c->d_queue.reserve(sizeof(int)) || !Dev::zero(c->d_queue.p, sizeof(int)))
+    return fail(c, RELEM_ENOMEM, "queue allocation failed");
+  return RELEM_OK;
+}
+
+void model_views(relem_ctx* c, ModelView& nullm, ModelView& m) {
+  m.h = c->dh; m.p = c->dpar; m.en = c->den;
+  nullm.h = c->dnull; nullm.p = c->dnullpar; nullm.en = c->den;
+}
+
+BatchView batch_view(const relem_batch* b) {
+  BatchView v;
+  v.nseq = b->nseq; v.seq = b->d_seq.as<unsigned char>(); v.off = b->d_off.as<long long>();
+  v.ws = b->d_ws.as<double>(); v.kind = b->d_kind.as<unsigned char>(); v.order = b->d_order.as<int>();
+  return v;
+}
+
+#ifndef RELEM_HOST_EMU
+struct Timer {
+  relem_ctx* c; const char* name; cudaEvent_t a, b;
+  Timer(relem_ctx* c_, const char* n) : c(c_), name(n) {
+    cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream);
+  }
+  void stop() {
+    cudaEventRecord(b, c->stream); cudaEventSynchronize(b);
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    c->timing.push_back(TimingEntry{name, ms, 1});
+    cudaEventDestroy(a); cudaEventDestroy(b);
+  }
+};
+#else
+struct Timer { Timer(relem_ctx* c, const char* n) { c->timing.push_back(TimingEntry{n, 0.f, 1}); } void stop() {} };
+#endif
+
+int ready(relem_ctx* c) {
+  if (!c) return RELEM_EINVAL;
+  if (!c->have_energy) return fail(c, RELEM_EINVAL, "relem_set_energy has not been called");
+  if (!c->have_pattern) return fail(c, RELEM_EINVAL, "relem_set_pattern has not been called");
+  if (!c->have_params) return fail(c, RELEM_EINVAL, "relem_set_params has not been called");
+  if (c->no_rss) return fail(c, RELEM_EINVAL, "the --no-rss linear model is not built in this round");
+  return RELEM_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================= ABI
+extern "C" {
+
+const char* relem_version(void) {
+#ifdef RELEM_HOST_EMU
+  return "relem-b200 0.1 (HOST EMULATION - debug only)";
+#else
+  return "relem-b200 0.1 (sm_100a)";
+#endif
+}
+
+int relem_create(relem_ctx** out, int device_ordinal) {
+  if (!out) return RELEM_EINVAL;
+  *out = nullptr;
+#ifndef RELEM_HOST_EMU
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, RELEM_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                          " (librelem has no CPU path)");
+  if (device_ordinal < 0 || device_ordinal >= n) return fail(nullptr, RELEM_EINVAL, "bad device ordinal");
+  e = cudaSetDevice(device_ordinal);
+  if (e != cudaSuccess) return fail(nullptr, RELEM_ECUDA, cudaGetErrorString(e));
+#endif
+  relem_ctx* c = new relem_ctx();
+  c->dev = device_ordinal;
+#ifndef RELEM_HOST_EMU
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) { delete c; return fail(nullptr, RELEM_ECUDA, "cudaGetDeviceProperties"); }
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; return fail(nullptr, RELEM_ECUDA, "cudaStreamCreate"); }
+#endif
+  c->nullflat.null_model();
+  std::vector<double> z4(4, 0.);
+  if (!upload_hmm(c->nullflat, c->d_null, c->dnull) || !upload(c->d_null_theta, z4)) {
+    delete c;
+    return fail(nullptr, RELEM_ENOMEM, "device allocation failed");
+  }
+  c->dnullpar.theta = c->d_null_theta.as<double>(); c->dnullpar.n_theta = 4;
+  c->dnullpar.lambda0 = 1.; c->dnullpar.lambda1 = 1.; c->dnullpar.ltau = 0.; c->dnullpar.no_prf = 1;
+  *out = c;
+  return RELEM_OK;
+}
+
+void relem_destroy(relem_ctx* c) {
+  if (!c) return;
+#ifndef RELEM_HOST_EMU
+  cudaSetDevice(c->dev);
+  if (c->nccl_comm && c->nccl_lib) {
+    typedef int (*destroy_t)(void*);
+    destroy_t f = (destroy_t)dlsym(c->nccl_lib, "ncclCommDestroy");
+    if (f) f(c->nccl_comm);
+  }
+  c->d_coll.release();
+#endif
+  DevBuf* all[] = {&c->d_energy, &c->d_codes, &c->d_hmm, &c->d_null, &c->d_n2s, &c->d_theta, &c->d_null_theta,
+                   &c->d_scratch, &c->d_queue, &c->d_res, &c->d_Z, &c->d_ENo, &c->d_ENx, &c->d_EH, &c->d_eff,
+                   &c->d_skip, &c->d_s1, &c->d_s2, &c->d_s3, &c->d_s4, &c->d_s5, &c->d_s6, &c->d_s7, &c->d_s8,
+                   &c->d_s9, &c->d_s10};
+  for (DevBuf* b : all) b->release();
+#ifndef RELEM_HOST_EMU
+  if (c->stream) cudaStreamDestroy(c->stream);
+#endif
+  delete c;
+}
+
+const char* relem_last_error(const relem_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int relem_set_energy(relem_ctx* c, const char* param, int max_span, int max_iloop, double min_bpp, int no_ene) {
+  if (!c || !param) return RELEM_EINVAL;
+  if (max_span < 0 || min_bpp < 0) return fail(c, RELEM_EINVAL, "bad max_span / min_bpp");
+  EnergyInts ints;
+  std::string name(param);
+  if (!builtin_energy_ints(name, ints)) {
+    std::ifstream ifs(name.c_str());
+    if (!ifs) return fail(c, RELEM_EIO, "cannot open param file: " + name);
+    std::stringstream ss; ss << ifs.rdbuf();
+    std::string err;
+    if (!parse_param_text(ss.str(), ints, err)) return fail(c, RELEM_EIO, "failed parsing energy parameter: " + err);
+  }
+  c->et.build(ints);
+  c->max_span = max_span; c->max_iloop = max_iloop; c->min_bpp = min_bpp; c->no_ene = no_ene ? 1 : 0;
+  if (!upload_energy(c)) return fail(c, RELEM_ENOMEM, "energy upload failed");
+  c->have_energy = true;
+  return RELEM_OK;
+}
+
+int relem_set_pattern(relem_ctx* c, const char* pattern, int no_rss, int no_prf) {
+  if (!c || !pattern) return RELEM_EINVAL;
+  if (no_rss && no_prf) return fail(c, RELEM_EINVAL, "no-rss, no-profile are exclusive.");
+  try {
+    c->hmm.build(pattern);
+  } catch (std::exception& e) {
+    return fail(c, RELEM_EINVAL, e.what());
+  }
+  if (no_rss && std::string(pattern).find(')') != std::string::npos)
+    return fail(c, RELEM_EINVAL, "search pattern must not include pair when no-rss mode");
+  c->flat.from(c->hmm);
+  c->no_rss = no_rss ? 1 : 0; c->no_prf = no_prf ? 1 : 0;
+  c->n_theta = c->hmm.n_theta();
+  std::vector<int> n2s;
+  for (auto& r : c->hmm.n2s) n2s.insert(n2s.end(), r.begin(), r.end());
+  if (!upload_hmm(c->flat, c->d_hmm, c->dh) || !upload(c->d_n2s, n2s) ||
+      !c->d_theta.reserve(sizeof(double) * c->n_theta))
+    return fail(c, RELEM_ENOMEM, "automaton upload failed");
+  c->have_pattern = true;
+  c->have_params = false;
+  return RELEM_OK;
+}
+
+int relem_model_dims(const relem_ctx* c, int* M, int* S, int* n_rows, int* n_theta) {
+  if (!c || !c->have_pattern) return RELEM_EINVAL;
+  if (M) *M = c->hmm.M;
+  if (S) *S = c->hmm.S;
+  if (n_rows) *n_rows = (int)c->hmm.row_size.size();
+  if (n_theta) *n_theta = c->n_theta;
+  return RELEM_OK;
+}
+
+int relem_theta_rows(const relem_ctx* c, int* row_sizes) {
+  if (!c || !c->have_pattern || !row_sizes) return RELEM_EINVAL;
+  for (size_t k = 0; k < c->hmm.row_size.size(); ++k) row_sizes[k] = c->hmm.row_size[k];
+  return RELEM_OK;
+}
+
+int relem_hmm_get(const relem_ctx* c, int kind, int* out) {
+  if (!c || !c->have_pattern) return -1;
+  const ProfileHMM& h = c->hmm;
+  std::vector<int> v;
+  auto csr = [&](const std::vector<std::vector<int>>& lists) {
+    int o = 0;
+    v.push_back(0);
+    for (auto& r : lists) { o += (int)r.size(); v.push_back(o); }
+    for (auto& r : lists) v.insert(v.end(), r.begin(), r.end());
+  };
+  switch (kind) {
+    case 0: for (auto& s : h.state) { v.push_back(s.l); v.push_back(s.r); } break;
+    case 1: v = h.loop_state; break;
+    case 2: csr(h.right); break;
+    case 3: csr(h.left); break;
+    case 4: csr(h.pairt); break;
+    case 5: for (auto& q : h.quads) v.insert(v.end(), q.begin(), q.end()); break;
+    case 6: v = h.node; break;
+    case 7: v = h.theta_id; break;
+    case 9: for (auto& r : h.reachable) for (char x : r) v.push_back(x); break;
+    default: return -1;
+  }
+  if (out) std::copy(v.begin(), v.end(), out);
+  return (int)v.size();
+}
+
+int relem_energy_get(const relem_ctx* c, const char* name, double* out, int cap) {
+  if (!c || !c->have_energy || !name) return -1;
+  const EnergyTables& t = c->et;
+  struct Ent { const char* n; const double* p; int len; };
+  const Ent ents[] = {
+      {"hairpin", t.hairpin, 31}, {"mismatch_h", &t.mismatch_h[0][0][0], 175}, {"mismatch_i", &t.mismatch_i[0][0][0], 175},
+      {"mismatch_m", &t.mismatch_m[0][0][0], 175}, {"mismatch_1ni", &t.mismatch_1ni[0][0][0], 175},
+      {"mismatch_23i", &t.mismatch_23i[0][0][0], 175}, {"mismatch_ext", &t.mismatch_ext[0][0][0], 175},
+      {"stack", &t.stack[0][0], 49}, {"bulge", t.bulge, 31}, {"term_au", &t.term_au, 1},
+      {"int11", &t.int11[0][0][0][0], 1600}, {"int21", &t.int21[0][0][0][0][0], 8000},
+      {"int22", &t.int22[0][0][0][0][0][0], 40000}, {"internal", t.internal, 31}, {"dangle5", &t.dangle5[0][0], 40},
+      {"dangle3", &t.dangle3[0][0], 40}, {"ninio", t.ninio, 31}, {"mlintern", &t.mlintern, 1},
+      {"mlclosing", &t.mlclosing, 1}, {"ml_base", &t.ml_base, 1}, {"lxc37", &t.lxc37, 1},
+      {"triloop", t.tri_w.data(), (int)t.tri_w.size()}, {"tetraloop", t.tetra_w.data(), (int)t.tetra_w.size()},
+      {"hexaloop", t.hexa_w.data(), (int)t.hexa_w.size()}};
+  for (const Ent& e : ents)
+    if (!std::strcmp(e.n, name)) {
+      int n = std::min(cap, e.len);
+      if (out) for (int k = 0; k < n; ++k) out[k] = e.p[k];
+      return e.len;
+    }
+  return -1;
+}
+
+int relem_set_params(relem_ctx* c, const double* theta_flat, int n_theta, const double lambda[2], double tau) {
+  if (!c || !theta_flat || !lambda) return RELEM_EINVAL;
+  if (!c->have_pattern) return fail(c, RELEM_EINVAL, "relem_set_pattern has not been called");
+  if (n_theta != c->n_theta) return fail(c, RELEM_EINVAL, "theta size does not match the pattern");
+  if (!Dev::h2d(c->d_theta.p, theta_flat, sizeof(double) * n_theta)) return fail(c, RELEM_ECUDA, "theta upload failed");
+  c->dpar.theta = c->d_theta.as<double>(); c->dpar.n_theta = n_theta;
+  c->dpar.lambda0 = lambda[0]; c->dpar.lambda1 = lambda[1]; c->dpar.ltau = std::log(tau); c->dpar.no_prf = c->no_prf;
+  c->have_params = true;
+  return RELEM_OK;
+}
+
+int relem_batch_create(relem_ctx* c, int nseq, const uint8_t* seq_cat, const int64_t* off, const double* ws_cat,
+                       const uint8_t* kind, const int32_t* gate, relem_batch** out) {
+  if (!c || !out || nseq < 0 || !off || (nseq > 0 && (!seq_cat || !ws_cat))) return RELEM_EINVAL;
+  if (!c->have_energy) return fail(c, RELEM_EINVAL, "relem_set_energy has not been called");
+  relem_batch* b = new relem_batch();
+  b->nseq = nseq;
+  b->off.assign(off, off + nseq + 1);
+  b->total_len = off[nseq] - off[0];
+  if (off[0] != 0) { delete b; return fail(c, RELEM_EINVAL, "off[0] must be 0"); }
+  std::vector<int> order(nseq);
+  std::iota(order.begin(), order.end(), 0);
+  for (int n = 0; n < nseq; ++n) {
+    long long L = off[n + 1] - off[n];
+    if (L < 1 || L > 9999) { delete b; return fail(c, RELEM_EINVAL, "sequence length must be in 1..9999"); }
+    b->Lmax = std::max<int>(b->Lmax, (int)L);
+    long long W = std::min<long long>(L, c->max_span);
+    b->cells += (L + 1) * (W + 1) - W * (W + 1) / 2;
+  }
+  for (long long k = 0; k < b->total_len; ++k)
+    if (seq_cat[k] > 4) { delete b; return fail(c, RELEM_EINVAL, "base codes must be 0..4"); }
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int a, int bb) { return off[a + 1] - off[a] > off[bb + 1] - off[bb]; });
+  b->kind.assign(nseq, 0);
+  if (kind) b->kind.assign(kind, kind + nseq);
+  b->gate.assign(nseq, -1);
+  if (gate) { b->gate.assign(gate, gate + nseq); b->has_gate = true; }
+  for (int n = 0; n < nseq; ++n) {
+    if (b->kind[n] > 2) { delete b; return fail(c, RELEM_EINVAL, "bad sequence kind"); }
+    if (b->gate[n] >= nseq || b->gate[n] == n) { delete b; return fail(c, RELEM_EINVAL, "bad gate index"); }
+  }
+  std::vector<unsigned char> seqv(seq_cat, seq_cat + b->total_len);
+  std::vector<double> wsv(ws_cat, ws_cat + b->total_len);
+  std::vector<long long> offv(off, off + nseq + 1);
+  if (!upload(b->d_seq, seqv) || !upload(b->d_ws, wsv) || !upload(b->d_off, offv) || !upload(b->d_kind, b->kind) ||
+      !upload(b->d_gate, b->gate) || !upload(b->d_order, order)) {
+    relem_batch_destroy(c, b);
+    return fail(c, RELEM_ENOMEM, "batch upload failed");
+  }
+  *out = b;
+  return RELEM_OK;
+}
+
+void relem_batch_destroy(relem_ctx*, relem_batch* b) {
+  if (!b) return;
+  b->d_seq.release(); b->d_off.release(); b->d_ws.release(); b->d_kind.release(); b->d_gate.release();
+  b->d_order.release();
+  delete b;
+}
+
+int64_t relem_batch_cells(const relem_batch* b) { return b ? b->cells : 0; }
+
+int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
+  int rc = ready(c);
+  if (rc) return rc;
+  if (!b || !out) return RELEM_EINVAL;
+  c->timing.clear();
+  const int NT = c->n_theta, nseq = b->nseq;
+  out->fn = 0; out->EH_diff[0] = out->EH_diff[1] = 0; out->sum_eff = 0; out->n_skipped = 0;
+  if (out->EN_diff) std::fill(out->EN_diff, out->EN_diff + NT, 0.);
+  if (nseq == 0) return RELEM_OK;
+#ifndef RELEM_HOST_EMU
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+#endif
+  Launch L;
+#ifdef RELEM_HOST_EMU
+  rc = plan_launch(c, b, 2, true, nullptr, L);
+#else
+  rc = plan_launch(c, b, 2, true, (const void*)relem_estep_kernel, L);
+#endif
+  if (rc) return rc;
+  int nres = 7 + 2 * NT;
+  if (!c->d_Z.reserve(sizeof(double) * 3 * nseq) || !c->d_ENo.reserve(sizeof(double) * (size_t)NT * nseq) ||
+      !c->d_ENx.reserve(sizeof(double) * (size_t)NT * nseq) || !c->d_EH.reserve(sizeof(double) * 4 * nseq) ||
+      !c->d_eff.reserve(sizeof(double) * nseq) || !c->d_skip.reserve(nseq) || !c->d_res.reserve(sizeof(double) * nres))
+    return fail(c, RELEM_ENOMEM, "output allocation failed");
+  EstepOut eo;
+  eo.Z = c->d_Z.as<double>(); eo.ENo = c->d_ENo.as<double>(); eo.ENx = c->d_ENx.as<double>();
+  eo.EH = c->d_EH.as<double>(); eo.bpp_eff = c->d_eff.as<double>(); eo.skipped = c->d_skip.as<unsigned char>();
+  ModelView nullm, m;
+  model_views(c, nullm, m);
+  BatchView bv = batch_view(b);
+  {
+    Timer t(c, "relem_estep_kernel");
+#ifdef RELEM_HOST_EMU
+    std::vector<unsigned char> smem(L.lay.sm_total + 64);
+    relem_estep_kernel(nullm, m, bv, L.lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), eo, smem.data());
+#else
+    relem_estep_kernel<<<L.nslots, 256, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
+                                                                      c->d_queue.as<int>(), eo);
+    CUDA_TRY(c, cudaGetLastError());
+#endif
+    t.stop();
+  }
+  {
+    Timer t(c, "relem_reduce_kernel");
+#ifdef RELEM_HOST_EMU
+    relem_reduce_kernel(nseq, NT, bv.kind, b->has_gate ? b->d_gate.as<int>() : nullptr, eo, c->d_res.as<double>(), nullptr);
+#else
+    relem_reduce_kernel<<<1, 256, 0, c->stream>>>(nseq, NT, bv.kind, b->has_gate ? b->d_gate.as<int>() : nullptr, eo,
+                                                  c->d_res.as<double>());
+    CUDA_TRY(c, cudaGetLastError());
+#endif
+    t.stop();
+  }
+#ifndef RELEM_HOST_EMU
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+#endif
+  std::vector<double> res(nres);
+  if (!Dev::d2h(res.data(), c->d_res.p, sizeof(double) * nres)) return fail(c, RELEM_ECUDA, "result copy failed");
+  out->fn = res[0]; out->sum_eff = res[1]; out->n_skipped = (int64_t)res[2];
+  out->EH_diff[0] = res[3] - res[5]; out->EH_diff[1] = res[4] - res[6];
+  if (out->EN_diff) for (int t = 0; t < NT; ++t) out->EN_diff[t] = res[7 + t] - res[7 + NT + t];
+  bool ok = true;
+  if (out->Z) ok = ok && Dev::d2h(out->Z, c->d_Z.p, sizeof(double) * 3 * nseq);
+  if (out->ENo) ok = ok && Dev::d2h(out->ENo, c->d_ENo.p, sizeof(double) * (size_t)NT * nseq);
+  if (out->ENx) ok = ok && Dev::d2h(out->ENx, c->d_ENx.p, sizeof(double) * (size_t)NT * nseq);
+  if (out->EH) ok = ok && Dev::d2h(out->EH, c->d_EH.p, sizeof(double) * 4 * nseq);
+  if (out->bpp_eff) ok = ok && Dev::d2h(out->bpp_eff, c->d_eff.p, sizeof(double) * nseq);
+  if (out->skipped) ok = ok && Dev::d2h(out->skipped, c->d_skip.p, nseq);
+  if (!ok) return fail(c, RELEM_ECUDA, "detail copy failed");
+  return RELEM_OK;
+}
+
+int relem_estep(relem_ctx* c, int nseq, const uint8_t* seq_cat, const int64_t* off, const double* ws_cat,
+                const uint8_t* kind, const int32_t* gate, relem_estep_out* out) {
+  relem_batch* b = nullptr;
+  int rc = relem_batch_create(c, nseq, seq_cat, off, ws_cat, kind, gate, &b);
+  if (rc) return rc;
+  rc = relem_estep_run(c, b, out);
+  relem_batch_destroy(c, b);
+  return rc;
+}
+
+int relem_bpp(relem_ctx* c, relem_batch* b, int64_t* moff, uint8_t* bp_ok, uint8_t* left_ok, double* lnbpp,
+              double* bpp_eff, double* lnZ) {
+  if (!c || !b || !moff) return RELEM_EINVAL;
+  if (!c->have_energy) return fail(c, RELEM_EINVAL, "relem_set_energy has not been called");
+  c->timing.clear();
+  const int nseq = b->nseq;
+  std::vector<long long> mo(nseq + 1, 0);
+  for (int n = 0; n < nseq; ++n) {
+    long long L = b->off[n + 1] - b->off[n], W = std::min<long long>(L, c->max_span);
+    mo[n + 1] = mo[n] + (L + 1) * (W + 1);
+  }
+  for (int n = 0; n <= nseq; ++n) moff[n] = mo[n];
+  if (nseq == 0) return RELEM_OK;
+#ifndef RELEM_HOST_EMU
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+#endif
+  // the filter pass needs no motif: run it with the null automaton in both model slots
+  ModelView nullm, m;
+  nullm.h = c->dnull; nullm.p = c->dnullpar; nullm.en = c->den;
+  m = nullm;
+  FlatHMM keep = c->flat; int keep_nt = c->n_theta;
+  c->flat = c->nullflat; c->n_theta = 4;
+  Launch L;
+#ifdef RELEM_HOST_EMU
+  int rc = plan_launch(c, b, 1, false, nullptr, L);
+#else
+  int rc = plan_launch(c, b, 1, false, (const void*)relem_bpp_kernel, L);
+#endif
+  c->flat = keep; c->n_theta = keep_nt;
+  if (rc) return rc;
+  size_t tot = (size_t)mo[nseq];
+  if (!c->d_s1.reserve(sizeof(long long) * (nseq + 1)) || !c->d_s2.reserve(tot) || !c->d_s3.reserve(tot) ||
+      !c->d_s4.reserve(lnbpp ? tot * sizeof(double) : 8) || !c->d_s5.reserve(sizeof(double) * nseq) ||
+      !c->d_s6.reserve(sizeof(double) * nseq))
+    return fail(c, RELEM_ENOMEM, "output allocation failed");
+  Dev::h2d(c->d_s1.p, mo.data(), sizeof(long long) * (nseq + 1));
+  BppOut bo;
+  bo.moff = c->d_s1.as<long long>(); bo.bp_ok = c->d_s2.as<unsigned char>(); bo.left_ok = c->d_s3.as<unsigned char>();
+  bo.lnbpp = lnbpp ? c->d_s4.as<double>() : nullptr; bo.bpp_eff = c->d_s5.as<double>(); bo.lnZ = c->d_s6.as<double>();
+  Dev::zero(c->d_s6.p, sizeof(double) * nseq);
+  BatchView bv = batch_view(b);
+  {
+    Timer t(c, "relem_bpp_kernel");
+#ifdef RELEM_HOST_EMU
+    std::vector<unsigned char> smem(L.lay.sm_total + 64);
+    relem_bpp_kernel(nullm, m, bv, L.lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), bo, smem.data());
+#else
+    relem_bpp_kernel<<<L.nslots, 256, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
+                                                                    c->d_queue.as<int>(), bo);
+    CUDA_TRY(c, cudaGetLastError());
+#endif
+    t.stop();
+  }
+#ifndef RELEM_HOST_EMU
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+#endif
+  bool ok = true;
+  if (bp_ok) ok = ok && Dev::d2h(bp_ok, bo.bp_ok, tot);
+  if (left_ok) ok = ok && Dev::d2h(left_ok, bo.left_ok, tot);
+  if (lnbpp) ok = ok && Dev::d2h(lnbpp, bo.lnbpp, tot * sizeof(double));
+  if (bpp_eff) ok = ok && Dev::d2h(bpp_eff, bo.bpp_eff, sizeof(double) * nseq);
+  if (lnZ) ok = ok && Dev::d2h(lnZ, bo.lnZ, sizeof(double) * nseq);
+  if (!ok) return fail(c, RELEM_ECUDA, "result copy failed");
+  return RELEM_OK;
+}
+
+int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
+  int rc = ready(c);
+  if (rc) return rc;
+  if (!b || !out) return RELEM_EINVAL;
+  c->timing.clear();
+  const int NT = c->n_theta, nseq = b->nseq;
+  if (out->EN) std::fill(out->EN, out->EN + NT, 0.);
+  if (nseq == 0) return RELEM_OK;
+#ifndef RELEM_HOST_EMU
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+#endif
+  Launch L;
+#ifdef RELEM_HOST_EMU
+  rc = plan_launch(c, b, 1, true, nullptr, L);
+#else
+  rc = plan_launch(c, b, 1, true, (const void*)relem_scan_kernel, L);
+#endif
+  if (rc) return rc;
+  size_t tl = (size_t)b->total_len;
+  if (!c->d_s1.reserve(sizeof(double) * tl) || !c->d_s2.reserve(sizeof(double) * (tl + nseq)) ||
+      !c->d_s3.reserve(sizeof(double) * tl) || !c->d_s4.reserve(sizeof(int) * tl) || !c->d_s5.reserve(tl) ||
+      !c->d_s6.reserve(sizeof(int) * nseq) || !c->d_s7.reserve(sizeof(int) * nseq) ||
+      !c->d_s8.reserve(sizeof(double) * nseq) || !c->d_s9.reserve(sizeof(double) * (size_t)NT * nseq) ||
+      !c->d_s10.reserve(sizeof(double) * nseq))
+    return fail(c, RELEM_ENOMEM, "output allocation failed");
+  ScanOut so;
+  so.PysL = c->d_s1.as<double>(); so.PyeL = c->d_s2.as<double>(); so.PyiL = c->d_s3.as<double>();
+  so.psihat = c->d_s4.as<int>(); so.rss = c->d_s5.as<char>(); so.Ys = c->d_s6.as<int>(); so.Ye = c->d_s7.as<int>();
+  so.exist = c->d_s8.as<double>(); so.EN = c->d_s9.as<double>(); so.ZL = c->d_s10.as<double>();
+  ModelView nullm, m;
+  model_views(c, nullm, m);
+  BatchView bv = batch_view(b);
+  {
+    Timer t(c, "relem_scan_kernel");
+#ifdef RELEM_HOST_EMU
+    std::vector<unsigned char> smem(L.lay.sm_total + 64);
+    relem_scan_kernel(nullm, m, bv, L.lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), c->d_n2s.as<int>(), so,
+                      smem.data());
+#else
+    relem_scan_kernel<<<L.nslots, 256, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
+                                                                     c->d_queue.as<int>(), c->d_n2s.as<int>(), so);
+    CUDA_TRY(c, cudaGetLastError());
+#endif
+    t.stop();
+  }
+#ifndef RELEM_HOST_EMU
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+#endif
+  bool ok = true;
+  if (out->PysL) ok = ok && Dev::d2h(out->PysL, so.PysL, sizeof(double) * tl);
+  if (out->PyeL) ok = ok && Dev::d2h(out->PyeL, so.PyeL, sizeof(double) * (tl + nseq));
+  if (out->PyiL) ok = ok && Dev::d2h(out->PyiL, so.PyiL, sizeof(double) * tl);
+  if (out->psihat) ok = ok && Dev::d2h(out->psihat, so.psihat, sizeof(int) * tl);
+  if (out->rss) ok = ok && Dev::d2h(out->rss, so.rss, tl);
+  if (out->Ys) ok = ok && Dev::d2h(out->Ys, so.Ys, sizeof(int) * nseq);
+  if (out->Ye) ok = ok && Dev::d2h(out->Ye, so.Ye, sizeof(int) * nseq);
+  if (out->exist_prob) ok = ok && Dev::d2h(out->exist_prob, so.exist, sizeof(double) * nseq);
+  if (out->ZL) ok = ok && Dev::d2h(out->ZL, so.ZL, sizeof(double) * nseq);
+  if (out->EN) {
+    // E[N] summed over the batch in input order (RNAelemScanDP::operator(), motif_scanner.hpp:253-258)
+    std::vector<double> en((size_t)NT * nseq);
+    ok = ok && Dev::d2h(en.data(), so.EN, sizeof(double) * en.size());
+    for (int n = 0; n < nseq; ++n) for (int t = 0; t < NT; ++t) out->EN[t] += en[(size_t)n * NT + t];
+  }
+  if (!ok) return fail(c, RELEM_ECUDA, "result copy failed");
+  return RELEM_OK;
+}
+
+int relem_scan(relem_ctx* c, int nseq, const uint8_t* seq_cat, const int64_t* off, const double* ws_cat,
+               relem_scan_out* out) {
+  relem_batch* b = nullptr;
+  int rc = relem_batch_create(c, nseq, seq_cat, off, ws_cat, nullptr, nullptr, &b);
+  if (rc) return rc;
+  rc = relem_scan_run(c, b, out);
+  relem_batch_destroy(c, b);
+  return rc;
+}
+
+void relem_assigned_range(int64_t total, int n, int k, int64_t* from, int64_t* to) {
+  // contiguous blocks, the remainder spread over the first ranks (arrayjob_manager.hpp:141-149)
+  int64_t base = n > 0 ? total / n : 0, rem = n > 0 ? total % n : 0;
+  int64_t f = base * k + std::min<int64_t>(k, rem);
+  int64_t t = f + base + (k < rem ? 1 : 0);
+  if (from) *from = f;
+  if (to) *to = t;
+}
+
+int relem_last_timing(const relem_ctx* c, const char** names, float* ms, int* launches, int cap) {
+  if (!c) return 0;
+  int n = std::min<int>(cap, (int)c->timing.size());
+  for (int k = 0; k < n; ++k) {
+    if (names) names[k] = c->timing[k].name;
+    if (ms) ms[k] = c->timing[k].ms;
+    if (launches) launches[k] = c->timing[k].launches;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------- NCCL
+#ifdef RELEM_HOST_EMU
+int relem_comm_unique_id(uint8_t*) { return RELEM_EINVAL; }
+int relem_comm_init(relem_ctx* c, const uint8_t*, int, int) { return fail(c, RELEM_EINVAL, "no collectives in the emulation"); }
+int relem_allreduce_sum(relem_ctx* c, double*, int) { return fail(c, RELEM_EINVAL, "no collectives in the emulation"); }
+#else
+namespace {
+void* nccl_open() {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    void* h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) return h;
+  }
+  return nullptr;
+}
+}  // namespace
+
+int relem_comm_unique_id(uint8_t id[128]) {
+  void* lib = nccl_open();
+  if (!lib) { g_create_error = "libnccl.so.2 not found"; return RELEM_EINVAL; }
+  typedef int (*fn_t)(void*);
+  fn_t f = (fn_t)dlsym(lib, "ncclGetUniqueId");
+  if (!f) { g_create_error = "ncclGetUniqueId not found"; return RELEM_EINVAL; }
+  return f(id) == 0 ? RELEM_OK : RELEM_ECUDA;
+}
+
+int relem_comm_init(relem_ctx* c, const uint8_t id[128], int rank, int nranks) {
+  if (!c || !id) return RELEM_EINVAL;
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  if (!c->nccl_lib) c->nccl_lib = nccl_open();
+  if (!c->nccl_lib) return fail(c, RELEM_EINVAL, "libnccl.so.2 not found");
+  struct Uid { char b[128]; } uid;
+  std::memcpy(uid.b, id, 128);
+  typedef int (*init_t)(void**, int, Uid, int);
+  init_t f = (init_t)dlsym(c->nccl_lib, "ncclCommInitRank");
+  if (!f) return fail(c, RELEM_EINVAL, "ncclCommInitRank not found");
+  int r = f(&c->nccl_comm, nranks, uid, rank);
+  if (r != 0) return fail(c, RELEM_ECUDA, "ncclCommInitRank failed: " + std::to_string(r));
+  return RELEM_OK;
+}
+
+int relem_allreduce_sum(relem_ctx* c, double* host_buf, int n) {
+  if (!c || !host_buf || n < 0) return RELEM_EINVAL;
+  if (!c->nccl_comm) return fail(c, RELEM_EINVAL, "relem_comm_init has not been called");
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  if (!c->d_coll.reserve(sizeof(double) * n)) return fail(c, RELEM_ENOMEM, "collective buffer");
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_coll.p, host_buf, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  typedef int (*ar_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  ar_t f = (ar_t)dlsym(c->nccl_lib, "ncclAllReduce");
+  if (!f) return fail(c, RELEM_EINVAL, "ncclAllReduce not found");
+  const int ncclDouble = 8, ncclSum = 0;
+  int r = f(c->d_coll.p, c->d_coll.p, (size_t)n, ncclDouble, ncclSum, c->nccl_comm, c->stream);
+  if (r != 0) return fail(c, RELEM_ECUDA, "ncclAllReduce failed: " + std::to_string(r));
+  CUDA_TRY(c, cudaMemcpyAsync(host_buf, c->d_coll.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return RELEM_OK;
+}
+#endif
+
+}  // extern "C"
