@@ -1,0 +1,34 @@
+"""CPU-side check of the kernel SOURCE logic through its single-thread host emulation (tests/emu): the same
+.cu/.cuh files, compiled by g++, against the golden outputs of the unmodified reference.  This does not replace
+the GPU parity tests (tests/test_gpu_parity.py); it exists so that a logic regression is caught in the GPU-less
+build container.  Kept to the small cases so the CPU suite stays fast."""
+import pytest
+
+import caselib
+import rnaelem_b200 as rb
+
+SMALL = ["m0", "m1", "m3", "ragged"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_estep_emulated(name, emu_lib):
+    case = caselib.load_case(name)
+    ctx = caselib.make_ctx(case, lib=emu_lib)
+    caselib.check_estep(case, ctx)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_scan_emulated(name, emu_lib):
+    case = caselib.load_case(name)
+    ctx = caselib.make_ctx(case, lib=emu_lib)
+    caselib.check_scan(case, ctx)
+
+
+def test_no_rss_is_refused(emu_lib):
+    case = caselib.load_case("m2")
+    ctx = caselib.make_ctx(case, lib=emu_lib)
+    seqs, wss = caselib.scan_inputs(case)
+    sc, off, wc = rb.pack_batch(seqs, wss)
+    b = ctx.batch(sc, off, wc)
+    with pytest.raises(rb.RelemError):
+        ctx.estep_run(b)
