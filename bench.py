@@ -243,6 +243,7 @@ def main_own(args):
         step_resident()
         tm = ctx.timing()
         kernel_ms.append([t for t in tm if t[0] == "relem_estep_kernel"][0][1])
+        phases = {t[0][6:]: round(t[1], 4) for t in tm if t[0].startswith("phase:")}
         launches += sum(t[2] for t in tm)
     barrier()
     t1 = time.perf_counter()
@@ -289,7 +290,8 @@ def main_own(args):
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "kernel": "relem_estep_kernel", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": which,
-                             "kernel_ms": kms, "algorithmic_bytes_per_launch": int(step_bytes)}}
+                             "kernel_ms": kms, "algorithmic_bytes_per_launch": int(step_bytes)},
+                "phase_share": phases}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             line["cpu_baseline"] = cpu_baseline(args.ref_sample or max(16, 4 * cores))

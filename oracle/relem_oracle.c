@@ -8,6 +8,7 @@
  * path and emission counts under its debug flags; test-exact.cpp:90-137 RNAfold dot plot) and the outputs of the
  * unmodified reference compiled into oracle/_ref (tests/golden/*).
  */
+#define _POSIX_C_SOURCE 200809L
 #include "relem_oracle.h"
 
 #include <math.h>
@@ -1103,6 +1104,25 @@ int orc_estep_seq(orc_model* m, const int* seq, int L, const double* ws, int res
   m->ZL = Zx; m->dEH = EHx; m->dEN = ENx;
   compute_outside(m, c_outside, c_after);
   if (Zx_out) *Zx_out = Zx;
+  return 0;
+}
+
+/* the reference's test fixture RNAelemDP::dp() (RNAelem-test/motif_test.hpp:26-34): inside, then one outside pass
+ * with the normaliser ZL given by the caller (its tests pass oneL = 0 to get un-normalised counts) */
+int orc_debug_eval(orc_model* m, const int* seq, int L, const double* ws, double ZL, double* pf, double* pf_out,
+                   double* EN, double* EH) {
+  set_seq(m, seq, L, NULL);
+  m->ws = ws;
+  alloc_tables(m);
+  init_inside(m); init_outside(m, 1, 1);
+  m->mode = MODE_TRAIN;
+  compute_inside(m, c_inside, c_before);
+  int np = orc_hmm_nparam(m);
+  memset(EN, 0, sizeof(double) * np); EH[0] = EH[1] = 0.;
+  m->ZL = ZL; m->dEH = EH; m->dEN = EN;
+  compute_outside(m, c_outside, c_after);
+  *pf = part_func(m, 1, 1);
+  *pf_out = OTAB(m->out_o, m, 0, N2S(m, 0, 0));
   return 0;
 }
 

@@ -20,6 +20,7 @@
 
 #ifdef RELEM_HOST_EMU
 #define RDEV inline
+#define RHD inline
 #define RCONST static const
 #define CTA_TID 0
 #define CTA_NTH 1
@@ -32,6 +33,7 @@ inline double d_add(double a, double b) { volatile double r = a + b; return r; }
 #else
 #include <cuda_runtime.h>
 #define RDEV __device__ __forceinline__
+#define RHD __host__ __device__ inline
 #define RCONST __constant__ const
 #define CTA_TID ((int)threadIdx.x)
 #define CTA_NTH ((int)blockDim.x)
@@ -78,6 +80,8 @@ struct DevHMM {
   const int *quad_off, *quad_s1, *quad_s2, *quad_s3;
   const int *split_off, *split_left, *split_right;
   const int *node, *theta_id, *theta_off;
+  const int *right_tgt, *left_tgt, *pair_tgt, *quad_tgt, *split_tgt;  // target state of each flat list entry
+  int n_right, n_left, n_pair, n_quad, n_split;
   int s00, s0M2, s0M1;
 };
 

@@ -6,10 +6,12 @@
 //   relem_bpp_kernel     K0 alone (EnergyModel::fill_bpp_tables, energy_model.hpp:211-266)
 #ifndef RELEM_DP_KERNELS_CUH
 #define RELEM_DP_KERNELS_CUH
-#include "dp_pass.cuh"
+#include "dp_warp.cuh"
 
 namespace relem {
 namespace dp {
+
+#define RELEM_CTA_THREADS 128
 
 struct BatchView {
   int nseq;
@@ -26,7 +28,8 @@ struct SlotLayout {
   unsigned long long tabA, Q0, Q1, tab0, q0, otab, QO0, QO1, otab0, QO00, emit0, emitT, zeros, G, stack;
   int Lmax, Wmax, mw;
   // dynamic shared memory carve-up (byte offsets)
-  int sm_x, sm_sp3, sm_sp4, sm_sp6, sm_bp, sm_lf, sm_bp2, sm_en, sm_pys, sm_pyi, sm_pye, sm_red, sm_total;
+  int sm_x, sm_sp3, sm_sp4, sm_sp6, sm_bp, sm_lf, sm_bp2, sm_en, sm_pys, sm_pyi, sm_pye, sm_red, sm_ctr, sm_warp, warp_bytes,
+      sm_total;
 };
 
 struct EstepOut {   // device arrays, per sequence
@@ -36,6 +39,7 @@ struct EstepOut {   // device arrays, per sequence
   double* EH;       // [nseq][4]
   double* bpp_eff;  // [nseq]
   unsigned char* skipped;
+  unsigned long long* prof;  // [16] cycles per phase summed over CTAs (thread 0 clocks), may be null
 };
 
 struct ScanOut {
@@ -167,6 +171,20 @@ RDEV void cta_fold_G(const ModelView& m, const SeqView& q, const double* G, doub
   }
 }
 
+#ifdef RELEM_HOST_EMU
+#define PROF_MARK(slot) ((void)0)
+#else
+// phase clock: thread 0 adds the cycles since the previous mark to prof[slot]
+#define PROF_MARK(slot)                                                        \
+  do {                                                                         \
+    if (CTA_TID == 0 && out.prof) {                                            \
+      long long now__ = clock64();                                             \
+      atomicAdd(out.prof + (slot), (unsigned long long)(now__ - prof_t0));     \
+      prof_t0 = now__;                                                         \
+    }                                                                          \
+  } while (0)
+#endif
+
 RDEV int claim(int* queue, int* sh) {
   if (CTA_TID == 0) {
 #ifdef RELEM_HOST_EMU
@@ -187,7 +205,7 @@ RDEV int claim(int* queue, int* sh) {
 #define RELEM_SMEM_ARG , unsigned char* smem_raw
 #define RELEM_BLOCK_IDX 0
 #else
-#define RELEM_KERNEL __global__ void __launch_bounds__(256)
+#define RELEM_KERNEL __global__ void __launch_bounds__(RELEM_CTA_THREADS)
 #define RELEM_SMEM_ARG
 #define RELEM_BLOCK_IDX ((int)blockIdx.x)
 #endif
@@ -201,19 +219,30 @@ RELEM_KERNEL relem_estep_kernel(ModelView nullm, ModelView m, BatchView b, SlotL
   Smem sm = carve(smem_raw, lay);
   double* slot = scratch + (unsigned long long)RELEM_BLOCK_IDX * lay.stride;
   const int S = m.h.S, NT = m.p.n_theta;
+  WarpSm wsm = warp_carve(smem_raw + lay.sm_warp + warp_id() * lay.warp_bytes, S, lay.Wmax);
+  int* ctr = (int*)(smem_raw + lay.sm_ctr);
+  if (CTA_TID == 0) { ctr[0] = 0; ctr[1] = 0; }
+  CTA_SYNC();
   for (;;) {
     int qi = claim(queue, (int*)(sm.red + 40));
     if (qi >= b.nseq) break;
     int n = b.order[qi];
     SeqView q;
     q.S = S;
+#ifndef RELEM_HOST_EMU
+    long long prof_t0 = clock64();
+#endif
     double eff = cta_prepare(nullm, m, b, n, lay, slot, sm, q, nullptr, nullptr);
+    PROF_MARK(0);
     double* emit0 = slot + lay.emit0; double* emitT = slot + lay.emitT;
     q.emit0 = emit0; q.emitT = emitT;
     cta_emit_tables(m, q, emit0, emitT);
     CTA_SYNC();
     double* tab = slot + lay.tabA; double* otab = slot + lay.otab;
-    cta_inside<false, NoConstraint>(m, q, tab, otab, nullptr, nullptr, NoConstraint());
+    double* Q0 = slot + lay.Q0; double* Q1 = slot + lay.Q1;
+    unsigned long long nt = (unsigned long long)NPLANE * q.cells * S;
+    cta_inside_warp(m, q, tab, otab, NoConstraint(), wsm, ctr, Q0, Q1, nt);
+    PROF_MARK(1);
     int L = q.L;
     double Ztt = part_func(m.h, otab, L, S, true, true);
     double Ztf = part_func(m.h, otab, L, S, true, false);
@@ -231,15 +260,13 @@ RELEM_KERNEL relem_estep_kernel(ModelView nullm, ModelView m, BatchView b, SlotL
       CTA_SYNC();
       continue;
     }
-    double* Q0 = slot + lay.Q0; double* Q1 = slot + lay.Q1;
     double* QO0 = slot + lay.QO0; double* QO1 = slot + lay.QO1;
     double* G = slot + lay.G;
-    unsigned long long nt = (unsigned long long)NPLANE * q.cells * S;
-    cta_zero(Q0, nt); cta_zero(Q1, nt);
     cta_zero(QO0, (unsigned long long)(L + 1) * S); cta_zero(QO1, (unsigned long long)(L + 1) * S);
     cta_zero(G, 2ull * m.h.M * L);
     cta_zero(sm.en, 2ull * NT);
     CTA_SYNC();
+    PROF_MARK(2);
     // channel 0: both boundary states open (Zo); channel 1: the restricted condition (Zx)
     double root[6];
     const DevHMM& h = m.h;
@@ -251,8 +278,9 @@ RELEM_KERNEL relem_estep_kernel(ModelView nullm, ModelView m, BatchView b, SlotL
     else { root[3] = (Zft > NINF) ? exp(r00 - Zft) : 0.; root[4] = 0.; root[5] = 0.; }
     Counts cn; cn.G = G; cn.ENp = sm.en; cn.Pys = cn.Pyi = cn.Pye = nullptr; cn.n_theta = NT; cn.ML = m.h.M * L;
     double eh[4];
-    cta_outside<2, HOOK_TRAIN, NoConstraint>(m, q, tab, otab, Q0, Q1, QO0, QO1, root, NoConstraint(), cn, eh);
+    cta_outside_warp<2, HOOK_TRAIN, false>(m, q, tab, otab, Q0, Q1, QO0, QO1, root, NoConstraint(), cn, eh, wsm, ctr);
     CTA_SYNC();
+    PROF_MARK(3);
     if (!m.p.no_prf) cta_fold_G(m, q, G, sm.en, 2);
     double e0 = cta_sum(eh[0], sm.red), e1 = cta_sum(eh[1], sm.red), e2 = cta_sum(eh[2], sm.red),
            e3 = cta_sum(eh[3], sm.red);
@@ -263,6 +291,7 @@ RELEM_KERNEL relem_estep_kernel(ModelView nullm, ModelView m, BatchView b, SlotL
     }
     if (CTA_TID == 0) { out.EH[n * 4 + 0] = e0; out.EH[n * 4 + 1] = e1; out.EH[n * 4 + 2] = e2; out.EH[n * 4 + 3] = e3; }
     CTA_SYNC();
+    PROF_MARK(4);
   }
 }
 
@@ -415,6 +444,10 @@ RELEM_KERNEL relem_scan_kernel(ModelView nullm, ModelView m, BatchView b, SlotLa
   double* slot = scratch + (unsigned long long)RELEM_BLOCK_IDX * lay.stride;
   const int S = m.h.S, NT = m.p.n_theta;
   const DevHMM& h = m.h;
+  WarpSm wsm = warp_carve(smem_raw + lay.sm_warp + warp_id() * lay.warp_bytes, S, lay.Wmax);
+  int* ctr = (int*)(smem_raw + lay.sm_ctr);
+  if (CTA_TID == 0) { ctr[0] = 0; ctr[1] = 0; }
+  CTA_SYNC();
   for (;;) {
     int qi = claim(queue, (int*)(sm.red + 40));
     if (qi >= b.nseq) break;
@@ -432,9 +465,9 @@ RELEM_KERNEL relem_scan_kernel(ModelView nullm, ModelView m, BatchView b, SlotLa
     double* Q0 = slot + lay.Q0; double* QO0 = slot + lay.QO0; double* G = slot + lay.G;
     unsigned long long nt = (unsigned long long)NPLANE * q.cells * S;
     // ---- start / inner posteriors (calc_motif_start_position, motif_scanner.hpp:186-193)
-    cta_inside<false, NoConstraint>(m, q, tab, otab, nullptr, nullptr, NoConstraint());
+    cta_inside_warp(m, q, tab, otab, NoConstraint(), wsm, ctr, Q0, (double*)nullptr, nt);
     double ZL = part_func(h, otab, L, S, true, true);
-    cta_zero(Q0, nt); cta_zero(QO0, (unsigned long long)(L + 1) * S); cta_zero(G, (unsigned long long)h.M * L);
+    cta_zero(QO0, (unsigned long long)(L + 1) * S); cta_zero(G, (unsigned long long)h.M * L);
     cta_zero(sm.en, (unsigned long long)NT); cta_zero(sm.pys, L); cta_zero(sm.pyi, L); cta_zero(sm.pye, L + 1);
     CTA_SYNC();
     double root[3];
@@ -444,7 +477,7 @@ RELEM_KERNEL relem_scan_kernel(ModelView nullm, ModelView m, BatchView b, SlotLa
     Counts cn; cn.G = G; cn.ENp = sm.en; cn.Pys = sm.pys; cn.Pyi = sm.pyi; cn.Pye = sm.pye; cn.n_theta = NT;
     cn.ML = h.M * L;
     double eh[2];
-    cta_outside<1, HOOK_SCAN_START, NoConstraint>(m, q, tab, otab, Q0, nullptr, QO0, nullptr, root, NoConstraint(), cn, eh);
+    cta_outside_warp<1, HOOK_SCAN_START, false>(m, q, tab, otab, Q0, nullptr, QO0, nullptr, root, NoConstraint(), cn, eh, wsm, ctr);
     CTA_SYNC();
     if (!m.p.no_prf) cta_fold_G(m, q, G, sm.en, 1);
     CTA_SYNC();
@@ -469,15 +502,15 @@ RELEM_KERNEL relem_scan_kernel(ModelView nullm, ModelView m, BatchView b, SlotLa
     int Ys = ish[0];
     // ---- end posteriors under the fixed start (calc_motif_end_position, :195-202)
     StartConstraint sc; sc.ys = Ys;
-    cta_inside<false, StartConstraint>(m, q, tab, otab, nullptr, nullptr, sc);
+    cta_inside_warp(m, q, tab, otab, sc, wsm, ctr, Q0, (double*)nullptr, nt);
     double ZeL = part_func(h, otab, L, S, true, true);
-    cta_zero(Q0, nt); cta_zero(QO0, (unsigned long long)(L + 1) * S);
+    cta_zero(QO0, (unsigned long long)(L + 1) * S);
     CTA_SYNC();
     bool zfin = ZeL > NINF && ZeL < -NINF;
     root[0] = (zfin && h.s00 >= 0) ? exp(otab[L * S + h.s00] - ZeL) : 0.;
     root[1] = (zfin && h.s0M2 >= 0) ? exp(otab[L * S + h.s0M2] - ZeL) : 0.;
     root[2] = (zfin && h.s0M1 >= 0) ? exp(otab[L * S + h.s0M1] - ZeL) : 0.;
-    cta_outside<1, HOOK_SCAN_END, StartConstraint>(m, q, tab, otab, Q0, nullptr, QO0, nullptr, root, sc, cn, eh);
+    cta_outside_warp<1, HOOK_SCAN_END, false>(m, q, tab, otab, Q0, nullptr, QO0, nullptr, root, sc, cn, eh, wsm, ctr);
     CTA_SYNC();
     for (int t = CTA_TID; t <= L; t += CTA_NTH) {
       double a = sm.pye[t];

@@ -43,6 +43,9 @@ inline SlotLayout make_layout(int Lmax, int max_span, int S, int M, int n_theta,
   lay.sm_en = sm(2 * n_theta * 8 + 8);
   lay.sm_pys = sm((Lmax + 1) * 8); lay.sm_pyi = sm((Lmax + 1) * 8); lay.sm_pye = sm((Lmax + 2) * 8);
   lay.sm_red = sm(64 * 8);
+  lay.sm_ctr = sm(16);
+  lay.warp_bytes = warp_sm_bytes(S, Wmax);
+  lay.sm_warp = sm(lay.warp_bytes * (RELEM_CTA_THREADS / 32));
   lay.sm_total = b;
   return lay;
 }

@@ -431,6 +431,12 @@ void FlatHMM::from(const ProfileHMM& h) {
       }
     split_off[s + 1] = (int)split_left.size();
   }
+  auto targets = [&](const std::vector<int>& off, std::vector<int>& tgt) {
+    tgt.clear();
+    for (int s = 0; s < S; ++s) for (int a = off[s]; a < off[s + 1]; ++a) tgt.push_back(s);
+  };
+  targets(right_off, right_tgt); targets(left_off, left_tgt); targets(pair_off, pair_tgt);
+  targets(quad_off, quad_tgt); targets(split_off, split_tgt);
   node = h.node; theta_id = h.theta_id;
   theta_off.assign(1, 0);
   for (int r : h.row_size) theta_off.push_back(theta_off.back() + r);
@@ -447,6 +453,7 @@ void FlatHMM::null_model() {
   pair_off = {0, 1}; pair_idx = {0};
   quad_off = {0, 1}; quad_s1 = {0}; quad_s2 = {0}; quad_s3 = {0};
   split_off = {0, 1}; split_left = {0}; split_right = {0};
+  right_tgt = {0}; left_tgt = {0}; pair_tgt = {0}; quad_tgt = {0}; split_tgt = {0};
   node = {'z'}; theta_id = {0}; theta_off = {0, 4};
   s00 = 0; s0M2 = -1; s0M1 = -1;
 }

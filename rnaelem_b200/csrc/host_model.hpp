@@ -86,6 +86,7 @@ struct FlatHMM {
   int M, S;
   std::vector<int> st_l, st_r, is_loop;
   std::vector<int> right_off, right_idx, left_off, left_idx, pair_off, pair_idx;
+  std::vector<int> right_tgt, left_tgt, pair_tgt, quad_tgt, split_tgt;  // target state of every flat entry
   std::vector<int> quad_off, quad_s1, quad_s2, quad_s3;
   std::vector<int> split_off, split_left, split_right;
   std::vector<int> node, theta_id, theta_off;  // theta_off[row] = offset of the row in theta_flat

@@ -100,6 +100,7 @@ struct relem_ctx {
   int no_rss = 0, no_prf = 0;
   int n_theta = 0;
   DevBuf d_energy, d_codes, d_hmm, d_null, d_n2s, d_theta, d_null_theta;
+  DevBuf d_prof;
   DevBuf d_scratch, d_queue, d_res, d_Z, d_ENo, d_ENx, d_EH, d_eff, d_skip;
   DevBuf d_s1, d_s2, d_s3, d_s4, d_s5, d_s6, d_s7, d_s8, d_s9, d_s10;
   DevEnergy den;
@@ -202,7 +203,8 @@ bool upload_hmm(const FlatHMM& f, DevBuf& buf, DevHMM& d) {
          o6 = put(f.left_off), o7 = put(f.left_idx), o8 = put(f.pair_off), o9 = put(f.pair_idx), o10 = put(f.quad_off),
          o11 = put(f.quad_s1), o12 = put(f.quad_s2), o13 = put(f.quad_s3), o14 = put(f.split_off),
          o15 = put(f.split_left), o16 = put(f.split_right), o17 = put(f.node), o18 = put(f.theta_id),
-         o19 = put(f.theta_off);
+         o19 = put(f.theta_off), o20 = put(f.right_tgt), o21 = put(f.left_tgt), o22 = put(f.pair_tgt),
+         o23 = put(f.quad_tgt), o24 = put(f.split_tgt);
   if (!upload(buf, blob)) return false;
   const int* b = buf.as<int>();
   d.M = f.M; d.S = f.S;
@@ -210,6 +212,9 @@ bool upload_hmm(const FlatHMM& f, DevBuf& buf, DevHMM& d) {
   d.left_off = b + o6; d.left_idx = b + o7; d.pair_off = b + o8; d.pair_idx = b + o9; d.quad_off = b + o10;
   d.quad_s1 = b + o11; d.quad_s2 = b + o12; d.quad_s3 = b + o13; d.split_off = b + o14; d.split_left = b + o15;
   d.split_right = b + o16; d.node = b + o17; d.theta_id = b + o18; d.theta_off = b + o19;
+  d.right_tgt = b + o20; d.left_tgt = b + o21; d.pair_tgt = b + o22; d.quad_tgt = b + o23; d.split_tgt = b + o24;
+  d.n_right = (int)f.right_idx.size(); d.n_left = (int)f.left_idx.size(); d.n_pair = (int)f.pair_idx.size();
+  d.n_quad = (int)f.quad_s1.size(); d.n_split = (int)f.split_left.size();
   d.s00 = f.s00; d.s0M2 = f.s0M2; d.s0M1 = f.s0M1;
   return true;
 }
@@ -234,7 +239,7 @@ int plan_launch(relem_ctx* c, const relem_batch* b, int nch, bool coupled, const
   if (L.lay.sm_total > 227 * 1024) return fail(c, RELEM_EINVAL, "sequence too long: masks do not fit shared memory");
   CUDA_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.lay.sm_total));
   int occ = 0;
-  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, L.lay.sm_total));
+  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, RELEM_CTA_THREADS, L.lay.sm_total));
   if (occ < 1) return fail(c, RELEM_ECUDA, "kernel cannot be resident (occupancy 0)");
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
@@ -347,7 +352,7 @@ void relem_destroy(relem_ctx* c) {
   }
   c->d_coll.release();
 #endif
-  DevBuf* all[] = {&c->d_energy, &c->d_codes, &c->d_hmm, &c->d_null, &c->d_n2s, &c->d_theta, &c->d_null_theta,
+  DevBuf* all[] = {&c->d_prof, &c->d_energy, &c->d_codes, &c->d_hmm, &c->d_null, &c->d_n2s, &c->d_theta, &c->d_null_theta,
                    &c->d_scratch, &c->d_queue, &c->d_res, &c->d_Z, &c->d_ENo, &c->d_ENx, &c->d_EH, &c->d_eff,
                    &c->d_skip, &c->d_s1, &c->d_s2, &c->d_s3, &c->d_s4, &c->d_s5, &c->d_s6, &c->d_s7, &c->d_s8,
                    &c->d_s9, &c->d_s10};
@@ -556,6 +561,9 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
   EstepOut eo;
   eo.Z = c->d_Z.as<double>(); eo.ENo = c->d_ENo.as<double>(); eo.ENx = c->d_ENx.as<double>();
   eo.EH = c->d_EH.as<double>(); eo.bpp_eff = c->d_eff.as<double>(); eo.skipped = c->d_skip.as<unsigned char>();
+  eo.prof = nullptr;
+  if (c->d_prof.reserve(16 * sizeof(unsigned long long)) && Dev::zero(c->d_prof.p, 16 * sizeof(unsigned long long)))
+    eo.prof = c->d_prof.as<unsigned long long>();
   ModelView nullm, m;
   model_views(c, nullm, m);
   BatchView bv = batch_view(b);
@@ -565,7 +573,7 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
     std::vector<unsigned char> smem(L.lay.sm_total + 64);
     relem_estep_kernel(nullm, m, bv, L.lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), eo, smem.data());
 #else
-    relem_estep_kernel<<<L.nslots, 256, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
+    relem_estep_kernel<<<L.nslots, RELEM_CTA_THREADS, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
                                                                       c->d_queue.as<int>(), eo);
     CUDA_TRY(c, cudaGetLastError());
 #endif
@@ -576,7 +584,7 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
 #ifdef RELEM_HOST_EMU
     relem_reduce_kernel(nseq, NT, bv.kind, b->has_gate ? b->d_gate.as<int>() : nullptr, eo, c->d_res.as<double>(), nullptr);
 #else
-    relem_reduce_kernel<<<1, 256, 0, c->stream>>>(nseq, NT, bv.kind, b->has_gate ? b->d_gate.as<int>() : nullptr, eo,
+    relem_reduce_kernel<<<1, RELEM_CTA_THREADS, 0, c->stream>>>(nseq, NT, bv.kind, b->has_gate ? b->d_gate.as<int>() : nullptr, eo,
                                                   c->d_res.as<double>());
     CUDA_TRY(c, cudaGetLastError());
 #endif
@@ -587,6 +595,15 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
 #endif
   std::vector<double> res(nres);
   if (!Dev::d2h(res.data(), c->d_res.p, sizeof(double) * nres)) return fail(c, RELEM_ECUDA, "result copy failed");
+  if (eo.prof) {
+    unsigned long long pr[16];
+    if (Dev::d2h(pr, eo.prof, sizeof(pr))) {
+      static const char* pn[5] = {"phase:prepare+bpp_filter", "phase:emit+inside", "phase:zero_Q", "phase:outside", "phase:fold+store"};
+      double tot = 0;
+      for (int k = 0; k < 5; ++k) tot += (double)pr[k];
+      for (int k = 0; k < 5; ++k) c->timing.push_back(TimingEntry{pn[k], tot > 0 ? (float)(pr[k] / tot) : 0.f, 0});
+    }
+  }
   out->fn = res[0]; out->sum_eff = res[1]; out->n_skipped = (int64_t)res[2];
   out->EH_diff[0] = res[3] - res[5]; out->EH_diff[1] = res[4] - res[6];
   if (out->EN_diff) for (int t = 0; t < NT; ++t) out->EN_diff[t] = res[7 + t] - res[7 + NT + t];
@@ -658,7 +675,7 @@ int relem_bpp(relem_ctx* c, relem_batch* b, int64_t* moff, uint8_t* bp_ok, uint8
     std::vector<unsigned char> smem(L.lay.sm_total + 64);
     relem_bpp_kernel(nullm, m, bv, L.lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), bo, smem.data());
 #else
-    relem_bpp_kernel<<<L.nslots, 256, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
+    relem_bpp_kernel<<<L.nslots, RELEM_CTA_THREADS, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
                                                                     c->d_queue.as<int>(), bo);
     CUDA_TRY(c, cudaGetLastError());
 #endif
@@ -716,7 +733,7 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
     relem_scan_kernel(nullm, m, bv, L.lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), c->d_n2s.as<int>(), so,
                       smem.data());
 #else
-    relem_scan_kernel<<<L.nslots, 256, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
+    relem_scan_kernel<<<L.nslots, RELEM_CTA_THREADS, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
                                                                      c->d_queue.as<int>(), c->d_n2s.as<int>(), so);
     CUDA_TRY(c, cudaGetLastError());
 #endif
