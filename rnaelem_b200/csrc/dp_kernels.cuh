@@ -6,21 +6,13 @@
 //   relem_bpp_kernel     K0 alone (EnergyModel::fill_bpp_tables, energy_model.hpp:211-266)
 #ifndef RELEM_DP_KERNELS_CUH
 #define RELEM_DP_KERNELS_CUH
+#include "dp_batch.hpp"
 #include "dp_warp.cuh"
 
 namespace relem {
 namespace dp {
 
 #define RELEM_CTA_THREADS 128
-
-struct BatchView {
-  int nseq;
-  const unsigned char* seq;   // concatenated base codes
-  const long long* off;       // [nseq+1]
-  const double* ws;           // concatenated position weights
-  const unsigned char* kind;  // [nseq]
-  const int* order;           // processing order (longest first)
-};
 
 // per-slot scratch, offsets in doubles from the slot base
 struct SlotLayout {
@@ -30,16 +22,6 @@ struct SlotLayout {
   // dynamic shared memory carve-up (byte offsets)
   int sm_x, sm_sp3, sm_sp4, sm_sp6, sm_bp, sm_lf, sm_bp2, sm_en, sm_pys, sm_pyi, sm_pye, sm_red, sm_ctr, sm_warp, warp_bytes,
       sm_total;
-};
-
-struct EstepOut {   // device arrays, per sequence
-  double* Z;        // [nseq][3]
-  double* ENo;      // [nseq][n_theta]
-  double* ENx;
-  double* EH;       // [nseq][4]
-  double* bpp_eff;  // [nseq]
-  unsigned char* skipped;
-  unsigned long long* prof;  // [16] cycles per phase summed over CTAs (thread 0 clocks), may be null
 };
 
 struct ScanOut {

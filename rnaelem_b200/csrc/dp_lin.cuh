@@ -1,0 +1,1265 @@
+// dp_lin.cuh -- the throughput path of the E-step: scaled LINEAR-space inside / outside in gather form.
+//
+// Why it exists.  The log-space passes (dp_enum/dp_pass/dp_warp.cuh) follow the reference term by term: one
+// exp per transition term, a log per table entry, posteriors pushed to children with fp64 atomics.  ncu showed
+// that path bound by instruction count and latency (profiles/r1_estep_logspace.md).  The partition function is
+// a polynomial in Boltzmann factors, so the same quantities can be computed with multiply-adds only:
+//
+//   * every table holds  a^(i,j,.) = exp(inside(i,j,.)) * kappa^(j-i)   with one per-base scale kappa chosen from
+//     the background emission row (all recurrences are homogeneous in the span: children spans + emitted bases
+//     add up to the parent span, so the scale never has to be tracked); the exterior row is scaled by kappa^j;
+//   * outside values are kept as  b^(x) = d lnZ-weight / d a^(x)  (so posterior(x) = a^(x) * b^(x), scale free),
+//     and every CHILD GATHERS from its parents (the reference scatters, motif_trainer.hpp:408-456): no atomics, results
+//     are bit-reproducible from run to run.  The automaton's lists are therefore kept twice, grouped by parent and
+//     grouped by child (lin_model.hpp);
+//   * tables are stored per state type in the orientation their readers sweep: "by left end" [i][d][s] or "by right
+//     end" [j][d][s] (multiloop splits read 1(i,.) along a row and 2(.,j) along a column; interior loops read the
+//     inner pair by its right end and the two unpaired flanks one in each orientation);
+//   * the difference ENo-ENx / EHo-EHx the trainer needs is linear in the root weights of the outside pass, so
+//     one pass with root weights (1/Zo - [allowed]/Zx) yields it directly (NCH = 1); NCH = 2 keeps the two boundary
+//     conditions apart for callers that ask for per-sequence detail.
+//
+// Work mapping: one CTA per sequence (persistent, queue), wavefront over the span d, one warp per band cell, the 32
+// lanes over the entries of a transition list (or over structural candidates: split points, inner / outer pairs,
+// found with bit-window extracts from the base-pair masks).  A sequence whose scaled values leave the fp64 range
+// (non-finite Z or counts) is flagged and re-run by the caller on the log-space path.
+//
+// Reference semantics: EnergyModel::compute_inside/outside (energy_model.hpp:340-547), RNAelem::InsideFun /
+// OutsideFun (motif_model.hpp:230-613), RNAelemTrainDP (motif_trainer.hpp:124-458), fill_bpp_tables
+// (energy_model.hpp:211-266).
+#ifndef RELEM_DP_LIN_CUH
+#define RELEM_DP_LIN_CUH
+#include "dp_prim.cuh"
+#include "lin_model.hpp"
+
+namespace relem {
+namespace lin {
+using namespace relem::dp;
+
+#define LIN_CAP 64  // structural candidates buffered per warp before the list lanes consume them
+
+struct LinEnergyScalars {  // linear-domain copies of the scalar energy terms
+  double term_au, mlintern, mlclosing;
+};
+
+struct LinCtx {
+  LinHMM h;
+  LinParams p;
+  DevEnergy en;  // log-Boltzmann tables (coupled passes: exp(lambda * tsc), and tsc itself for the lambda gradient)
+  DevEnergy el;  // the same tables exponentiated (energy-only filter pass, lambda = 1)
+  SeqView q;     // x, special hairpins, bp (by left end), lf (by left end), sizes
+  const unsigned* bpr;  // bp by right end: bit d of row j <-> pair (j-d, j)
+  const unsigned* lfr;  // left_bp_ok by right end
+  const double* wsf;    // exp(position weight) [L]
+  const double* k0pow;  // kappa0^u, u = 0..W+1
+  double k0, k0sq;
+  int Ceff;             // min(C, 30): loops longer than 30 have zero weight (energy_param.hpp:754-755)
+};
+
+RDEV size_t cidx(const SeqView& q, int row, int d) { return ((size_t)row * (size_t)q.W1 + (size_t)d) * (size_t)q.S; }
+RDEV size_t kidx(const SeqView& q, int row, int d) { return (size_t)row * (size_t)q.W1 + (size_t)d; }
+
+// n (1..32) mask bits of a row starting at bit lo; bits beyond the row read as 0
+RDEV unsigned win_bits(const unsigned* row, int mw, int lo, int n) {
+  int w = lo >> 5, sh = lo & 31;
+  unsigned a = w < mw ? row[w] : 0u, b = (w + 1) < mw ? row[w + 1] : 0u;
+  unsigned v = sh ? ((a >> sh) | (b << (32 - sh))) : a;
+  return n >= 32 ? v : (v & ((1u << n) - 1u));
+}
+RDEV bool row_bit(const unsigned* row, int d) { return (row[d >> 5] >> (d & 31)) & 1u; }
+
+// ---- linear-domain energies (products of exponentiated tables; 0 = forbidden).  Same case analysis as
+// e_sum_ext_m / e_hairpin / e_loop (dp_common.cuh), i.e. energy_param.hpp:686-795.
+RDEV double l_sum_ext_m(const DevEnergy& el, const SeqView& q, int i, int j, bool ext) {
+  int type = bp_type(q.x[i], q.x[j]);
+  double z = 1.;
+  bool has5 = i - 1 >= 0, has3 = j + 1 < q.L;
+  if (has5 && has3) {
+    const double* t = ext ? el.mismatch_ext : el.mismatch_m;
+    z = ld_ro(t + (type * 5 + q.x[i - 1]) * 5 + q.x[j + 1]);
+  } else {
+    if (has5) z *= ld_ro(el.dangle5 + type * 5 + q.x[i - 1]);
+    if (has3) z *= ld_ro(el.dangle3 + type * 5 + q.x[j + 1]);
+  }
+  if (type > 2) z *= el.term_au;
+  return z;
+}
+RDEV double l_hairpin(const DevEnergy& el, const SeqView& q, int i, int j) {
+  int d = j - i - 1;
+  if (d < 1) return 0.;
+  int type = bp_type(q.x[i], q.x[j]);
+  double z = ld_ro(el.hairpin_len + d);
+  if (d < 3) {
+  } else if (d == 3) {
+    int hit = q.sp3[i];
+    if (hit >= 0) return ld_ro(el.tri_w + hit);
+    if (type > 2) z *= el.term_au;
+  } else if (d == 4) {
+    int hit = q.sp4[i];
+    if (hit >= 0) return ld_ro(el.tetra_w + hit);
+  } else if (d == 6) {
+    int hit = q.sp6[i];
+    if (hit >= 0) return ld_ro(el.hexa_w + hit);
+  }
+  if (d > 3) z *= ld_ro(el.mismatch_h + (type * 5 + q.x[i + 1]) * 5 + q.x[j - 1]);
+  return z;
+}
+RDEV double l_loop(const DevEnergy& el, const SeqView& sq, int i, int j, int p, int q) {
+  const unsigned char* x = sq.x;
+  int type = bp_type(x[i], x[j]);
+  int type2 = bp_type(x[q], x[p]);
+  int u1 = p - i - 1, u2 = j - q - 1;
+  int u = u1 > u2 ? u1 : u2;
+  if (u1 < 0 || u2 < 0 || 30 < u1 + u2) return 0.;
+  if (u1 == 0 && u2 == 0) return ld_ro(el.stack + type * 7 + type2);
+  if (u1 == 0 || u2 == 0) {
+    double z = ld_ro(el.bulge + u);
+    if (u == 1) z *= ld_ro(el.stack + type * 7 + type2);
+    else {
+      if (type > 2) z *= el.term_au;
+      if (type2 > 2) z *= el.term_au;
+    }
+    return z;
+  }
+  if (u <= 2) {
+    if (u1 + u2 == 2) return ld_ro(el.int11 + ((type * 8 + type2) * 5 + x[i + 1]) * 5 + x[j - 1]);
+    if (u1 == 1 && u2 == 2)
+      return ld_ro(el.int21 + (((type * 8 + type2) * 5 + x[i + 1]) * 5 + x[q + 1]) * 5 + x[j - 1]);
+    if (u1 == 2 && u2 == 1)
+      return ld_ro(el.int21 + (((type2 * 8 + type) * 5 + x[q + 1]) * 5 + x[i + 1]) * 5 + x[p - 1]);
+    return ld_ro(el.int22 + ((((type * 8 + type2) * 5 + x[i + 1]) * 5 + x[p - 1]) * 5 + x[q + 1]) * 5 + x[j - 1]);
+  }
+  int du = u1 - u2; if (du < 0) du = -du;
+  const double* mm = (u1 == 1 || u2 == 1) ? el.mismatch_1ni : (u1 + u2 == 5) ? el.mismatch_23i : el.mismatch_i;
+  return ld_ro(el.internal + u1 + u2) * ld_ro(el.ninio + du) * ld_ro(mm + (type * 5 + x[i + 1]) * 5 + x[j - 1]) *
+         ld_ro(mm + (type2 * 5 + x[q + 1]) * 5 + x[p - 1]);
+}
+
+// ================================================================================= energy-only filter (K0)
+// Tables of the energy-only grammar (one motif state, no emissions): EnergyModel::calc_BPP (energy_model.hpp:188-193).
+// a: P (by right end), E, M, 1 (by left end), 2 (by right end); b: P, E, M, B (both orientations), 2.  L == 1.
+struct K0Tabs {
+  double *P, *E, *M, *o1, *o2, *O;
+  double *bP, *bE, *bM, *bBl, *bBr, *b2, *bO;
+};
+
+RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
+  const SeqView& q = c.q;
+  const DevEnergy& el = c.el;
+  const int j = i + d, lane = lane_id();
+  const bool ne = el.no_ene != 0;
+  const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
+  if (!(gP || gB || gM || gE)) return;
+  double vP = 0.;
+  if (gP) {
+    if (ok_E(q, i + 1, d - 2)) vP += t.E[kidx(q, i + 1, d - 2)];
+    if (ok_P(q, i + 1, d - 2)) vP += t.P[kidx(q, j - 1, d - 2)] * (ne ? 1. : l_loop(el, q, i, j - 1, i + 1, j - 2));
+    vP *= c.k0sq;
+  }
+  double vB = 0.;
+  if (gB) {
+    const unsigned* ri = q.lf + i * q.mw;
+    const unsigned* rj = c.lfr + j * q.mw;
+    for (int u0 = 0; u0 <= d; u0 += WARP_N) {
+      int u = u0 + lane;
+      if (u <= d && row_bit(ri, u) && row_bit(rj, d - u)) vB += t.o1[kidx(q, i, u)] * t.o2[kidx(q, j, d - u)];
+    }
+    vB = w_sum(vB);
+  }
+  double v2 = 0., v1 = 0.;
+  if (gB) {
+    if (ok_B(q, i, d - 1)) v2 += t.o2[kidx(q, j - 1, d - 1)] * c.k0;
+    if (gP) v2 += vP * (ne ? 1. : l_sum_ext_m(el, q, i, j - 1, false) * el.mlintern);
+    v1 = v2 + vB;
+  }
+  double vM = 0.;
+  if (gM) {
+    if (ok_M(q, i + 1, d - 1)) vM += t.M[kidx(q, i + 1, d - 1)] * c.k0;
+    if (gB) vM += vB;
+  }
+  double vE = 0.;
+  if (gE) {
+    const int C = c.Ceff;
+    const int lo = d - C > 0 ? d - C : 0;
+    double acc = 0.;
+    for (int u10 = 0; u10 <= C; u10 += WARP_N) {
+      int u1 = u10 + lane, k = i + u1;
+      unsigned m = 0u;
+      if (u1 <= C && d - u1 >= lo) {
+        m = win_bits(q.bp + k * q.mw, q.mw, lo, d - u1 - lo + 1);
+        if (u1 == 0) m &= ~(1u << (d - lo));
+      }
+      while (m) {
+        int b = w_ffs(m) - 1;
+        m &= m - 1;
+        int dd = lo + b, l = k + dd, u2 = d - u1 - dd;
+        acc += t.P[kidx(q, l, dd)] * c.k0pow[u1 + u2] * (ne ? 1. : l_loop(el, q, i - 1, j, k, l - 1));
+      }
+    }
+    vE = w_sum(acc);
+    if (gM) vE += vM * (ne ? 1. : l_sum_ext_m(el, q, j, i - 1, false) * (el.mlclosing * el.mlintern));
+    if (d >= 1) vE += c.k0pow[d] * (ne ? 1. : l_hairpin(el, q, i - 1, j));
+  }
+  if (lane == 0) {
+    if (gP) t.P[kidx(q, j, d)] = vP;
+    if (gB) { t.o1[kidx(q, i, d)] = v1; t.o2[kidx(q, j, d)] = v2; }
+    if (gM) t.M[kidx(q, i, d)] = vM;
+    if (gE) t.E[kidx(q, i, d)] = vE;
+  }
+}
+
+// exterior row, one warp: O(j) = sum_i O(i) P(i,j) ext(i,j-1) + O(j-1)
+RDEV void k0_inside_ext(const LinCtx& c, const K0Tabs& t) {
+  const SeqView& q = c.q;
+  const DevEnergy& el = c.el;
+  const int L = q.L, lane = lane_id();
+  const bool ne = el.no_ene != 0;
+  if (lane == 0) t.O[0] = 1.;
+  w_sync();
+  for (int j = 1; j <= L; ++j) {
+    const unsigned* rj = c.bpr + j * q.mw;
+    int dmax = q.W < j ? q.W : j;
+    double acc = 0.;
+    for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
+      int u = u0 + lane;
+      if (u <= dmax && row_bit(rj, u))
+        acc += t.O[j - u] * t.P[kidx(q, j, u)] * (ne ? 1. : l_sum_ext_m(el, q, j - u, j - 1, true));
+    }
+    acc = w_sum(acc);
+    if (lane == 0) t.O[j] = acc + t.O[j - 1] * c.k0;
+    w_sync();
+  }
+}
+RDEV void k0_outside_ext(const LinCtx& c, const K0Tabs& t, double rootw) {
+  const SeqView& q = c.q;
+  const DevEnergy& el = c.el;
+  const int L = q.L, lane = lane_id();
+  const bool ne = el.no_ene != 0;
+  if (lane == 0) t.bO[L] = rootw;
+  w_sync();
+  for (int i = L - 1; i >= 0; --i) {
+    const unsigned* ri = q.bp + i * q.mw;
+    int dmax = q.W < L - i ? q.W : L - i;
+    double acc = 0.;
+    for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
+      int u = u0 + lane;
+      if (u <= dmax && row_bit(ri, u))
+        acc += t.bO[i + u] * t.P[kidx(q, i + u, u)] * (ne ? 1. : l_sum_ext_m(el, q, i, i + u - 1, true));
+    }
+    acc = w_sum(acc);
+    if (lane == 0) t.bO[i] = acc + t.bO[i + 1] * c.k0;
+    w_sync();
+  }
+}
+
+RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
+  const SeqView& q = c.q;
+  const DevEnergy& el = c.el;
+  const int j = i + d, lane = lane_id(), L = q.L, W = q.W;
+  const bool ne = el.no_ene != 0;
+  const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
+  if (!(gP || gB || gM || gE)) return;
+  double bE = 0.;
+  if (gE) bE = t.bP[kidx(q, i - 1, d + 2)] * c.k0sq;
+  double bM = 0.;
+  if (gM) {
+    if (gE) bM += bE * (ne ? 1. : l_sum_ext_m(el, q, j, i - 1, false) * (el.mlclosing * el.mlintern));
+    if (ok_M(q, i - 1, d + 1)) bM += t.bM[kidx(q, i - 1, d + 1)] * c.k0;
+  }
+  double b1 = 0., bB = 0., b2 = 0.;
+  if (gB) {
+    {  // this cell as the left child 1(i,k=j) of B(i,j')
+      const unsigned* ri = q.lf + i * q.mw;
+      const unsigned* rk = q.lf + j * q.mw;
+      int dmax = W < L - i ? W : L - i;
+      for (int d20 = d; d20 <= dmax; d20 += WARP_N) {
+        int d2 = d20 + lane;
+        if (d2 <= dmax && row_bit(ri, d2) && row_bit(rk, d2 - d)) b1 += t.bBl[kidx(q, i, d2)] * t.o2[kidx(q, i + d2, d2 - d)];
+      }
+      b1 = w_sum(b1);
+    }
+    bB = b1 + (gM ? bM : 0.);
+    {  // this cell as the right child 2(k=i,j) of B(i',j)
+      const unsigned* rj = c.lfr + j * q.mw;
+      int dmax = W < j ? W : j;
+      for (int d20 = d; d20 <= dmax; d20 += WARP_N) {
+        int d2 = d20 + lane, i2 = j - d2;
+        if (d2 <= dmax && row_bit(rj, d2) && row_bit(q.lf + i2 * q.mw, d2 - d))
+          b2 += t.bBr[kidx(q, j, d2)] * t.o1[kidx(q, i2, d2 - d)];
+      }
+      b2 = w_sum(b2) + b1;
+    }
+    if (ok_B(q, i, d + 1)) b2 += t.b2[kidx(q, i, d + 1)] * c.k0;
+  }
+  double bP = 0.;
+  if (gP) {
+    if (gB) bP += b2 * (ne ? 1. : l_sum_ext_m(el, q, i, j - 1, false) * el.mlintern);
+    if (ok_P(q, i - 1, d + 2)) bP += t.bP[kidx(q, i - 1, d + 2)] * c.k0sq * (ne ? 1. : l_loop(el, q, i - 1, j, i, j - 1));
+    bP += t.O[i] * t.bO[j] * (ne ? 1. : l_sum_ext_m(el, q, i, j - 1, true));
+    // enclosing pairs: this cell is the inner pair (k=i,l=j) of E(i',j')
+    const int C = c.Ceff;
+    const int hi = W < d + C + 2 ? W : d + C + 2;
+    double acc = 0.;
+    for (int u10 = 0; u10 <= C; u10 += WARP_N) {
+      int u1 = u10 + lane, i2 = i - u1, lo = d + u1 + 2;
+      unsigned m = 0u;
+      if (u1 <= C && i2 >= 1 && hi >= lo) {
+        m = win_bits(q.bp + (i2 - 1) * q.mw, q.mw, lo, hi - lo + 1);
+        if (u1 == 0) m &= ~1u;
+      }
+      while (m) {
+        int u2 = w_ffs(m) - 1;
+        m &= m - 1;
+        int j2 = j + u2;
+        acc += t.bE[kidx(q, i2, d + u1 + u2)] * c.k0pow[u1 + u2] * (ne ? 1. : l_loop(el, q, i2 - 1, j2, i, j - 1));
+      }
+    }
+    bP += w_sum(acc);
+  }
+  if (lane == 0) {
+    if (gP) t.bP[kidx(q, i, d)] = bP;
+    if (gE) t.bE[kidx(q, i, d)] = bE;
+    if (gM) t.bM[kidx(q, i, d)] = bM;
+    if (gB) { t.bBl[kidx(q, i, d)] = bB; t.bBr[kidx(q, j, d)] = bB; t.b2[kidx(q, i, d)] = b2; }
+  }
+}
+
+// ================================================================================= coupled passes
+struct CTabs {
+  double *aP, *aE, *aM, *a1, *a2, *aLl, *aLr, *aO;          // aP, a2, aLr by right end; the rest by left end
+  double *bP, *bEl, *bEr, *bM, *bBl, *bBr, *b2, *bL, *bO;   // bEr, bBr by right end; channel c at + c*bch (bO: + c*boch)
+  size_t bch, boch;
+};
+
+struct WarpLin {
+  double* curA;   // [NPLANE][S] inside values of the current cell
+  double* curB;   // [NCH][NPLANE][S] outside values of the current cell
+  double* partA;  // [NCH][n_max] per-entry partial sums
+  double* partT;  // [NCH][n_max] per-entry partial sums weighted by the transition energy
+  int *bi, *bj;   // candidate buffer
+  double *bt, *bf0, *bf1;
+  int* kbuf;      // [W+2] compacted split points
+  double* cntR;   // [NCH][n_right*5] emission posterior sums per (entry, base), private to the warp
+  double* cntL;   // [NCH][n_left*5]
+  double* pcnt;   // [NCH][n_pair*25] CTA-shared (atomics)
+  int n_max;
+};
+RHD int warp_lin_bytes(int S, int Wmax, int nch, int n_max, int n_right, int n_left) {
+  int n = (NPLANE * S + nch * NPLANE * S + 2 * nch * n_max + 3 * LIN_CAP + nch * 5 * (n_right + n_left)) * 8 +
+          (2 * LIN_CAP + Wmax + 4) * 4;
+  return (n + 15) & ~15;
+}
+RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n_max, int n_right, int n_left) {
+  WarpLin w;
+  double* p = (double*)base;
+  w.curA = p; p += NPLANE * S;
+  w.curB = p; p += nch * NPLANE * S;
+  w.partA = p; p += nch * n_max;
+  w.partT = p; p += nch * n_max;
+  w.bt = p; p += LIN_CAP;
+  w.bf0 = p; p += LIN_CAP;
+  w.bf1 = p; p += LIN_CAP;
+  w.cntR = p; p += nch * 5 * n_right;
+  w.cntL = p; p += nch * 5 * n_left;
+  int* ip = (int*)p;
+  w.bi = ip; ip += LIN_CAP;
+  w.bj = ip; ip += LIN_CAP;
+  w.kbuf = ip;
+  (void)Wmax;
+  w.pcnt = nullptr;
+  w.n_max = n_max;
+  return w;
+}
+
+RDEV double seg_sum(const double* part, const int* off, int s) {
+  double v = 0.;
+  for (int a = ld_ro(off + s), e = ld_ro(off + s + 1); a < e; ++a) v += part[a];
+  return v;
+}
+
+// all lanes call; lanes with ok append (ia, ib, tsc) and the two Boltzmann factors exp(lambda_slot * tsc)
+RDEV void batch_push(const LinCtx& c, WarpLin& w, int& n, bool ok, int ia, int ib, double tsc) {
+  unsigned bal = w_ballot(ok);
+  if (ok) {
+    int pos = n + w_popc(bal & lanemask_lt());
+    w.bi[pos] = ia; w.bj[pos] = ib; w.bt[pos] = tsc;
+    w.bf0[pos] = exp(c.p.lambda0 * tsc);
+    w.bf1[pos] = exp(c.p.lambda1 * tsc);
+  }
+  n += w_popc(bal);
+}
+#define LIN_ROOM(n, flush)                            \
+  if ((n) > LIN_CAP - WARP_N) {                       \
+    w_sync();                                         \
+    flush(n);                                         \
+    (n) = 0;                                          \
+    w_sync();                                         \
+  }
+
+// inner pairs (k,l) of E(i,j): u1 = k-i, u2 = j-l, u1+u2 <= C, not both 0 (energy_model.hpp:413-426)
+template <class F> RDEV void walk_inner(const LinCtx& c, int i, int d, WarpLin& w, F flush) {
+  const SeqView& q = c.q;
+  const int j = i + d, C = c.Ceff, lane = lane_id();
+  const int lo = d - C > 0 ? d - C : 0;
+  int n = 0;
+  for (int u10 = 0; u10 <= C; u10 += WARP_N) {
+    int u1 = u10 + lane, k = i + u1;
+    unsigned m = 0u;
+    if (u1 <= C && d - u1 >= lo) {
+      m = win_bits(q.bp + k * q.mw, q.mw, lo, d - u1 - lo + 1);
+      if (u1 == 0) m &= ~(1u << (d - lo));
+    }
+    while (w_any(m != 0u)) {
+      LIN_ROOM(n, flush)
+      bool has = m != 0u;
+      int b = 0;
+      if (has) { b = w_ffs(m) - 1; m &= m - 1; }
+      int l = k + lo + b;
+      double tsc = 0.;
+      bool ok = has;
+      if (has && !c.en.no_ene) { tsc = e_loop(c.en, q, i - 1, j, k, l - 1); ok = tsc > NINF; }
+      batch_push(c, w, n, ok, k, l, tsc);
+    }
+  }
+  w_sync();
+  if (n) flush(n);
+  w_sync();
+}
+// enclosing pairs: E(i',j') that have (k=i,l=j) as inner pair
+template <class F> RDEV void walk_outer(const LinCtx& c, int i, int d, WarpLin& w, F flush) {
+  const SeqView& q = c.q;
+  const int j = i + d, C = c.Ceff, lane = lane_id(), W = q.W;
+  const int hi = W < d + C + 2 ? W : d + C + 2;
+  int n = 0;
+  for (int u10 = 0; u10 <= C; u10 += WARP_N) {
+    int u1 = u10 + lane, i2 = i - u1, lo = d + u1 + 2;
+    unsigned m = 0u;
+    if (u1 <= C && i2 >= 1 && hi >= lo) {
+      m = win_bits(q.bp + (i2 - 1) * q.mw, q.mw, lo, hi - lo + 1);
+      if (u1 == 0) m &= ~1u;
+    }
+    while (w_any(m != 0u)) {
+      LIN_ROOM(n, flush)
+      bool has = m != 0u;
+      int u2 = 0;
+      if (has) { u2 = w_ffs(m) - 1; m &= m - 1; }
+      int j2 = j + u2;
+      double tsc = 0.;
+      bool ok = has;
+      if (has && !c.en.no_ene) { tsc = e_loop(c.en, q, i2 - 1, j2, i, j - 1); ok = tsc > NINF; }
+      batch_push(c, w, n, ok, i2, j2, tsc);
+    }
+  }
+  w_sync();
+  if (n) flush(n);
+  w_sync();
+}
+// cell (i,k) as the left unpaired flank L(i,k) of E(i,j') with inner pair (k,l); pushes (l, j')
+template <class F> RDEV void walk_left_flank(const LinCtx& c, int i, int d, WarpLin& w, F flush) {
+  const SeqView& q = c.q;
+  const int k = i + d, C = c.Ceff, lane = lane_id(), W = q.W;
+  const unsigned* rk = q.bp + k * q.mw;
+  const unsigned* ri = q.bp + (i - 1) * q.mw;
+  int n = 0;
+  for (int dd0 = 0; dd0 <= W; dd0 += WARP_N) {
+    int dd = dd0 + lane, l = k + dd;
+    unsigned m = 0u;
+    int lo = d + dd + 2;
+    if (dd <= W && row_bit(rk, dd)) {
+      int hi = W < lo + C - d ? W : lo + C - d;
+      if (hi >= lo) m = win_bits(ri, q.mw, lo, hi - lo + 1);
+    }
+    while (w_any(m != 0u)) {
+      LIN_ROOM(n, flush)
+      bool has = m != 0u;
+      int u2 = 0;
+      if (has) { u2 = w_ffs(m) - 1; m &= m - 1; }
+      int j2 = l + u2;
+      double tsc = 0.;
+      bool ok = has;
+      if (has && !c.en.no_ene) { tsc = e_loop(c.en, q, i - 1, j2, k, l - 1); ok = tsc > NINF; }
+      batch_push(c, w, n, ok, l, j2, tsc);
+    }
+  }
+  w_sync();
+  if (n) flush(n);
+  w_sync();
+}
+// cell (l,j) as the right unpaired flank L(l,j) of E(i',j) with inner pair (k,l); pushes (k, i')
+template <class F> RDEV void walk_right_flank(const LinCtx& c, int l, int d, WarpLin& w, F flush) {
+  const SeqView& q = c.q;
+  const int j = l + d, C = c.Ceff, lane = lane_id(), W = q.W;
+  const unsigned* rl = c.bpr + l * q.mw;
+  const unsigned* rj = c.bpr + (j + 1) * q.mw;
+  int n = 0;
+  for (int dd0 = 0; dd0 <= W; dd0 += WARP_N) {
+    int dd = dd0 + lane, k = l - dd;
+    unsigned m = 0u;
+    int lo = d + dd + 2;
+    if (dd <= W && k >= 0 && row_bit(rl, dd)) {
+      int hi = W < lo + C - d ? W : lo + C - d;
+      if (hi >= lo) m = win_bits(rj, q.mw, lo, hi - lo + 1);
+    }
+    while (w_any(m != 0u)) {
+      LIN_ROOM(n, flush)
+      bool has = m != 0u;
+      int u1 = 0;
+      if (has) { u1 = w_ffs(m) - 1; m &= m - 1; }
+      int i2 = k - u1;
+      double tsc = 0.;
+      bool ok = has;
+      if (has && !c.en.no_ene) { tsc = e_loop(c.en, q, i2 - 1, j, k, l - 1); ok = tsc > NINF; }
+      batch_push(c, w, n, ok, k, i2, tsc);
+    }
+  }
+  w_sync();
+  if (n) flush(n);
+  w_sync();
+}
+
+// ------------------------------------------------------------------------------------------------- inside
+RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
+  const LinHMM& h = c.h;
+  const LinParams& p = c.p;
+  const SeqView& q = c.q;
+  const int S = q.S, j = i + d, lane = lane_id();
+  double* cur = w.curA;
+  double* part = w.partA;
+  const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
+  const bool ne = c.en.no_ene != 0;
+  const int xl = i < q.L ? q.x[i] : 0, xr = d >= 1 ? q.x[j - 1] : 0;
+  const double wsl = i < q.L ? c.wsf[i] : 1., wsr = d >= 1 ? c.wsf[j - 1] : 1.;
+  // ---- L(i,j,s) <- L(i,j-1,s1) emitR
+  if (d == 0) {
+    for (int s = lane; s < S; s += WARP_N) cur[PL_L * S + s] = ld_ro(h.slot + s) ? 0. : 1.;
+  } else {
+    const double* src = t.aLl + cidx(q, i, d - 1);
+    for (int a = lane; a < h.n_right; a += WARP_N) {
+      int fl = ld_ro(h.r_flag + a);
+      double v = 0.;
+      if (fl & 2) {
+        v = src[ld_ro(h.r_src + a)] * ld_ro(p.r_w + a * 5 + xr);
+        if (fl & 1) v *= wsr;
+      }
+      part[a] = v;
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) cur[PL_L * S + s] = seg_sum(part, h.r_off, s);
+  }
+  w_sync();
+  // ---- P(i,j,s) <- E(i+1,j-1,s1) | P(i+1,j-1,s1)
+  if (gP) {
+    const bool cE = ok_E(q, i + 1, d - 2), cP = ok_P(q, i + 1, d - 2);
+    bool cPP = cP;
+    double f0 = 1., f1 = 1.;
+    if (cP && !ne) {
+      double tsc = e_loop(c.en, q, i, j - 1, i + 1, j - 2);
+      cPP = tsc > NINF;
+      if (cPP) { f0 = exp(p.lambda0 * tsc); f1 = exp(p.lambda1 * tsc); }
+    }
+    const double* srcE = t.aE + cidx(q, i + 1, d - 2);
+    const double* srcP = t.aP + cidx(q, j - 1, d - 2);
+    for (int a = lane; a < h.n_pair; a += WARP_N) {
+      double v = 0.;
+      if (cE || cPP) {
+        int fl = ld_ro(h.p_flag + a), s1 = ld_ro(h.p_src + a);
+        double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr);
+        if (fl & 1) wt *= wsl;
+        if (fl & 2) wt *= wsr;
+        if (cE) v += srcE[s1] * wt;
+        if (cPP) v += srcP[s1] * wt * (ld_ro(h.slot + ld_ro(h.p_tgt + a)) ? f1 : f0);
+      }
+      part[a] = v;
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) cur[PL_P * S + s] = seg_sum(part, h.p_off, s);
+    w_sync();
+  }
+  if (gB) {
+    // ---- B(i,j,s) <- 1(i,k,(s.l,h)) 2(k,j,(h,s.r))
+    int nk = 0;
+    {
+      const unsigned* ri = q.lf + i * q.mw;
+      const unsigned* rj = c.lfr + j * q.mw;
+      for (int u0 = 0; u0 <= d; u0 += WARP_N) {
+        int u = u0 + lane;
+        bool ok = u <= d && row_bit(ri, u) && row_bit(rj, d - u);
+        unsigned bal = w_ballot(ok);
+        if (ok) w.kbuf[nk + w_popc(bal & lanemask_lt())] = u;
+        nk += w_popc(bal);
+      }
+      w_sync();
+    }
+    const double* r1 = t.a1 + cidx(q, i, 0);
+    const double* r2 = t.a2 + cidx(q, j, 0);
+    for (int a = lane; a < h.n_split; a += WARP_N) {
+      int sl = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
+      double v = 0.;
+      for (int tt = 0; tt < nk; ++tt) {
+        int u = w.kbuf[tt];
+        v += r1[(size_t)u * S + sl] * r2[(size_t)(d - u) * S + sr];
+      }
+      part[a] = v;
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) cur[PL_B * S + s] = seg_sum(part, h.sp_off, s);
+    w_sync();
+    // ---- 2(i,j,s) <- 2(i,j-1,s1) emitR | P(i,j,s);  1 <- 2 | B
+    const bool ok2 = ok_B(q, i, d - 1);
+    const double* src2 = t.a2 + cidx(q, j - 1, d >= 1 ? d - 1 : 0);
+    for (int a = lane; a < h.n_right; a += WARP_N) {
+      double v = 0.;
+      if (ok2) {
+        v = src2[ld_ro(h.r_src + a)] * ld_ro(p.r_w + a * 5 + xr);
+        if (ld_ro(h.r_flag + a) & 1) v *= wsr;
+      }
+      part[a] = v;
+    }
+    bool c2P = gP;
+    double f0 = 1., f1 = 1.;
+    if (gP && !ne) {
+      double tsc = e_sum_ext_m(c.en, q, i, j - 1, false) + c.en.mlintern;
+      c2P = tsc > NINF;
+      if (c2P) { f0 = exp(p.lambda0 * tsc); f1 = exp(p.lambda1 * tsc); }
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) {
+      double x = seg_sum(part, h.r_off, s);
+      if (c2P) x += cur[PL_P * S + s] * (ld_ro(h.slot + s) ? f1 : f0);
+      cur[PL_2 * S + s] = x;
+      cur[PL_1 * S + s] = x + cur[PL_B * S + s];
+    }
+    w_sync();
+  }
+  // ---- M(i,j,s) <- M(i+1,j,s1) emitL | B(i,j,s)
+  if (gM) {
+    const bool okM = ok_M(q, i + 1, d - 1);
+    const double* srcM = t.aM + cidx(q, i + 1, d - 1);
+    for (int a = lane; a < h.n_left; a += WARP_N) {
+      double v = 0.;
+      if (okM) {
+        v = srcM[ld_ro(h.l_src + a)] * ld_ro(p.l_w + a * 5 + xl);
+        if (ld_ro(h.l_flag + a) & 1) v *= wsl;
+      }
+      part[a] = v;
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) {
+      double x = seg_sum(part, h.l_off, s);
+      if (gB) x += cur[PL_B * S + s];
+      cur[PL_M * S + s] = x;
+    }
+    w_sync();
+  }
+  // ---- E(i,j,s) <- M(i,j,s) | L(i,j,s) hairpin | P(k,l,s1) L(i,k,s2) L(l,j,s3)
+  if (gE) {
+    for (int a = lane; a < h.n_quad; a += WARP_N) part[a] = 0.;
+    w_sync();
+    if (h.n_quad > 0) {
+      const double* rL = t.aLl + cidx(q, i, 0);
+      const double* rR = t.aLr + cidx(q, j, 0);
+      walk_inner(c, i, d, w, [&](int n) {
+        for (int a = lane; a < h.n_quad; a += WARP_N) {
+          int s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a), s3 = ld_ro(h.q_s3 + a);
+          const double* bf = ld_ro(h.slot + ld_ro(h.q_tgt + a)) ? w.bf1 : w.bf0;
+          double v = part[a];
+          for (int pp = 0; pp < n; ++pp) {
+            int k = w.bi[pp], l = w.bj[pp];
+            double a0 = t.aP[cidx(q, l, l - k) + s1];
+            v += a0 * rL[(size_t)(k - i) * S + s2] * rR[(size_t)(j - l) * S + s3] * bf[pp];
+          }
+          part[a] = v;
+        }
+      });
+    }
+    bool cM = gM, cH = true;
+    double m0 = 1., m1 = 1., h0 = 1., h1 = 1.;
+    if (!ne) {
+      if (gM) {
+        double tM = e_sum_ext_m(c.en, q, j, i - 1, false) + (c.en.mlclosing + c.en.mlintern);
+        cM = tM > NINF;
+        if (cM) { m0 = exp(p.lambda0 * tM); m1 = exp(p.lambda1 * tM); }
+      }
+      double tH = e_hairpin(c.en, q, i - 1, j);
+      cH = tH > NINF;
+      if (cH) { h0 = exp(p.lambda0 * tH); h1 = exp(p.lambda1 * tH); }
+    }
+    for (int s = lane; s < S; s += WARP_N) {
+      double x = seg_sum(part, h.q_off, s);
+      int sl = ld_ro(h.slot + s);
+      if (cM) x += cur[PL_M * S + s] * (sl ? m1 : m0);
+      if (cH && ld_ro(h.is_loop + s)) x += cur[PL_L * S + s] * (sl ? h1 : h0);
+      cur[PL_E * S + s] = x;
+    }
+    w_sync();
+  }
+  // ---- write back
+  {
+    size_t il = cidx(q, i, d), ir = cidx(q, j, d);
+    for (int s = lane; s < S; s += WARP_N) {
+      double vL = cur[PL_L * S + s];
+      t.aLl[il + s] = vL;
+      t.aLr[ir + s] = vL;
+      if (gP) t.aP[ir + s] = cur[PL_P * S + s];
+      if (gB) { t.a1[il + s] = cur[PL_1 * S + s]; t.a2[ir + s] = cur[PL_2 * S + s]; }
+      if (gM) t.aM[il + s] = cur[PL_M * S + s];
+      if (gE) t.aE[il + s] = cur[PL_E * S + s];
+    }
+  }
+  w_sync();
+}
+
+// exterior row, one warp: O(j,s) <- O(i,(s.l,h)) P(i,j,(h,s.r)) ext | O(j-1,s1) emitR
+RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
+  const LinHMM& h = c.h;
+  const LinParams& p = c.p;
+  const SeqView& q = c.q;
+  const int S = q.S, L = q.L, lane = lane_id();
+  const bool ne = c.en.no_ene != 0;
+  double* part = w.partA;
+  double* cur = w.curA;
+  for (int s = lane; s < S; s += WARP_N) t.aO[s] = (s == h.s00) ? 1. : 0.;
+  w_sync();
+  for (int j = 1; j <= L; ++j) {
+    for (int a = lane; a < h.n_split; a += WARP_N) part[a] = 0.;
+    w_sync();
+    auto flush = [&](int n) {
+      for (int a = lane; a < h.n_split; a += WARP_N) {
+        int sl = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
+        const double* bf = ld_ro(h.slot + ld_ro(h.sp_tgt + a)) ? w.bf1 : w.bf0;
+        double v = part[a];
+        for (int pp = 0; pp < n; ++pp) {
+          int i = w.bi[pp];
+          v += t.aO[(size_t)i * S + sl] * t.aP[cidx(q, j, j - i) + sr] * bf[pp];
+        }
+        part[a] = v;
+      }
+    };
+    {
+      const unsigned* rj = c.bpr + j * q.mw;
+      int dmax = q.W < j ? q.W : j, n = 0;
+      for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
+        LIN_ROOM(n, flush)
+        int u = u0 + lane;
+        bool ok = u <= dmax && row_bit(rj, u);
+        double tsc = 0.;
+        if (ok && !ne) { tsc = e_sum_ext_m(c.en, q, j - u, j - 1, true); ok = tsc > NINF; }
+        batch_push(c, w, n, ok, j - u, j, tsc);
+      }
+      w_sync();
+      if (n) flush(n);
+      w_sync();
+    }
+    for (int s = lane; s < S; s += WARP_N) cur[s] = seg_sum(part, h.sp_off, s);
+    w_sync();
+    const int xr = q.x[j - 1];
+    const double wsr = c.wsf[j - 1];
+    for (int a = lane; a < h.n_right; a += WARP_N) {
+      double v = t.aO[(size_t)(j - 1) * S + ld_ro(h.r_src + a)] * ld_ro(p.r_w + a * 5 + xr);
+      if (ld_ro(h.r_flag + a) & 1) v *= wsr;
+      part[a] = v;
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) t.aO[(size_t)j * S + s] = cur[s] + seg_sum(part, h.r_off, s);
+    w_sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ outside
+// eh[c*2+slot]: lambda-gradient sums (sum of tsc * posterior), per lane, reduced by the caller
+template <int NCH> struct EhAcc {
+  double v[NCH * 2];
+  RDEV void add(int c, int slot, double x) {
+    v[c * 2] += slot ? 0. : x;
+    v[c * 2 + 1] += slot ? x : 0.;
+  }
+};
+
+// exterior row top-down, one warp.  bO(L,.) must hold the root weights.
+template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
+  const LinHMM& h = c.h;
+  const LinParams& p = c.p;
+  const SeqView& q = c.q;
+  const int S = q.S, L = q.L, lane = lane_id(), NM = w.n_max;
+  const bool ne = c.en.no_ene != 0;
+  for (int i = L - 1; i >= 0; --i) {
+    for (int a = lane; a < h.n_split; a += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
+    w_sync();
+    auto flush = [&](int n) {
+      for (int pz = lane; pz < h.n_split; pz += WARP_N) {
+        int a = ld_ro(h.spL_ord + pz);
+        int s = ld_ro(h.sp_tgt + a), sr = ld_ro(h.sp_r + a);
+        const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
+        double v[NCH];
+        for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
+        for (int pp = 0; pp < n; ++pp) {
+          int j = w.bi[pp];
+          double term = t.aP[cidx(q, j, j - i) + sr] * bf[pp];
+          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bO[ch * t.boch + (size_t)j * S + s] * term;
+        }
+        for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+      }
+    };
+    {
+      const unsigned* ri = q.bp + i * q.mw;
+      int dmax = q.W < L - i ? q.W : L - i, n = 0;
+      for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
+        LIN_ROOM(n, flush)
+        int u = u0 + lane;
+        bool ok = u <= dmax && row_bit(ri, u);
+        double tsc = 0.;
+        if (ok && !ne) { tsc = e_sum_ext_m(c.en, q, i, i + u - 1, true); ok = tsc > NINF; }
+        batch_push(c, w, n, ok, i + u, i, tsc);
+      }
+      w_sync();
+      if (n) flush(n);
+      w_sync();
+    }
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) w.curB[ch * S + s] = seg_sum(w.partA + ch * NM, h.spL_off, s);
+    w_sync();
+    // O(i+1,sp) -> O(i,s1) emitting x[i]
+    const int xr = q.x[i];
+    const double wsr = c.wsf[i];
+    for (int pz = lane; pz < h.n_right; pz += WARP_N) {
+      int a = ld_ro(h.rT_ord + pz);
+      int sp = ld_ro(h.r_tgt + a), ch_s = ld_ro(h.r_src + a);
+      double wt = ld_ro(p.r_w + a * 5 + xr);
+      if (ld_ro(h.r_flag + a) & 1) wt *= wsr;
+      double ac = t.aO[(size_t)i * S + ch_s];
+      for (int ch = 0; ch < NCH; ++ch) {
+        double contrib = t.bO[ch * t.boch + (size_t)(i + 1) * S + sp] * wt;
+        w.partA[ch * NM + pz] = contrib;
+        if (!p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
+      }
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch)
+        t.bO[ch * t.boch + (size_t)i * S + s] = w.curB[ch * S + s] + seg_sum(w.partA + ch * NM, h.rT_off, s);
+    w_sync();
+  }
+}
+
+template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w, EhAcc<NCH>& eh) {
+  const LinHMM& h = c.h;
+  const LinParams& p = c.p;
+  const SeqView& q = c.q;
+  const int S = q.S, j = i + d, lane = lane_id(), L = q.L, W = q.W, NM = w.n_max;
+  const bool ne = c.en.no_ene != 0;
+  const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
+  double* cA = w.curA;
+  double* cB = w.curB;
+#define CB(ch, pl, s) cB[((ch) * NPLANE + (pl)) * S + (s)]
+  const size_t il = cidx(q, i, d), ir = cidx(q, j, d);
+  // inside values of this cell (for the posteriors that are counted)
+  for (int s = lane; s < S; s += WARP_N) {
+    cA[PL_L * S + s] = t.aLl[il + s];
+    cA[PL_P * S + s] = gP ? t.aP[ir + s] : 0.;
+    cA[PL_2 * S + s] = gB ? t.a2[ir + s] : 0.;
+    cA[PL_M * S + s] = gM ? t.aM[il + s] : 0.;
+    cA[PL_E * S + s] = gE ? t.aE[il + s] : 0.;
+    for (int ch = 0; ch < NCH; ++ch) {
+      CB(ch, PL_E, s) = 0.; CB(ch, PL_M, s) = 0.; CB(ch, PL_1, s) = 0.; CB(ch, PL_B, s) = 0.;
+      CB(ch, PL_2, s) = 0.; CB(ch, PL_P, s) = 0.; CB(ch, PL_L, s) = 0.;
+    }
+  }
+  w_sync();
+  // ---- E(i,j,s1) <- parent P(i-1,j+1,s) (pair emission at i-1 and j)
+  if (gE) {
+    const int xl = q.x[i - 1], xr = q.x[j];
+    const double wsl = c.wsf[i - 1], wsr = c.wsf[j];
+    const size_t pb = cidx(q, i - 1, d + 2);
+    for (int pz = lane; pz < h.n_pair; pz += WARP_N) {
+      int a = ld_ro(h.pT_ord + pz);
+      int s = ld_ro(h.p_tgt + a), s1 = ld_ro(h.p_src + a), fl = ld_ro(h.p_flag + a);
+      double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr);
+      if (fl & 1) wt *= wsl;
+      if (fl & 2) wt *= wsr;
+      double ac = cA[PL_E * S + s1];
+      for (int ch = 0; ch < NCH; ++ch) {
+        double contrib = t.bP[ch * t.bch + pb + s] * wt;
+        w.partA[ch * NM + pz] = contrib;
+        double post = contrib * ac;
+        if (!p.no_prf && post != 0.) sm_add(w.pcnt + (ch * h.n_pair + a) * 25 + xl * 5 + xr, post);
+      }
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_E, s) = seg_sum(w.partA + ch * NM, h.pT_off, s);
+    w_sync();
+  }
+  // ---- M(i,j,s) <- E(i,j,s) | parent M(i-1,j,sp) emitting x[i-1]
+  if (gM) {
+    bool cM = gE;
+    double tM = 0., m0 = 1., m1 = 1.;
+    if (gE && !ne) {
+      tM = e_sum_ext_m(c.en, q, j, i - 1, false) + (c.en.mlclosing + c.en.mlintern);
+      cM = tM > NINF;
+      if (cM) { m0 = exp(p.lambda0 * tM); m1 = exp(p.lambda1 * tM); }
+    }
+    const bool okM = ok_M(q, i - 1, d + 1);
+    if (okM) {
+      const int xl = q.x[i - 1];
+      const double wsl = c.wsf[i - 1];
+      const size_t pb = cidx(q, i - 1, d + 1);
+      for (int pz = lane; pz < h.n_left; pz += WARP_N) {
+        int a = ld_ro(h.lT_ord + pz);
+        int sp = ld_ro(h.l_tgt + a), s1 = ld_ro(h.l_src + a);
+        double wt = ld_ro(p.l_w + a * 5 + xl);
+        if (ld_ro(h.l_flag + a) & 1) wt *= wsl;
+        double ac = cA[PL_M * S + s1];
+        for (int ch = 0; ch < NCH; ++ch) {
+          double contrib = t.bM[ch * t.bch + pb + sp] * wt;
+          w.partA[ch * NM + pz] = contrib;
+          if (!p.no_prf) w.cntL[(ch * h.n_left + a) * 5 + xl] += contrib * ac;
+        }
+      }
+      w_sync();
+    }
+    for (int s = lane; s < S; s += WARP_N) {
+      int sl = ld_ro(h.slot + s);
+      for (int ch = 0; ch < NCH; ++ch) {
+        double x = okM ? seg_sum(w.partA + ch * NM, h.lT_off, s) : 0.;
+        if (cM) {
+          double y = CB(ch, PL_E, s) * (sl ? m1 : m0);
+          x += y;
+          eh.add(ch, sl, tM * y * cA[PL_M * S + s]);
+        }
+        CB(ch, PL_M, s) = x;
+      }
+    }
+    w_sync();
+  }
+  if (gB) {
+    // ---- 1(i,j,sl): left child of B(i,j',s) with right sibling 2(j,j',sr)
+    {
+      int nk = 0;
+      const unsigned* ri = q.lf + i * q.mw;
+      const unsigned* rk = q.lf + j * q.mw;
+      int dmax = W < L - i ? W : L - i;
+      for (int d20 = d; d20 <= dmax; d20 += WARP_N) {
+        int d2 = d20 + lane;
+        bool ok = d2 <= dmax && row_bit(ri, d2) && row_bit(rk, d2 - d);
+        unsigned bal = w_ballot(ok);
+        if (ok) w.kbuf[nk + w_popc(bal & lanemask_lt())] = d2;
+        nk += w_popc(bal);
+      }
+      w_sync();
+      const size_t rb = cidx(q, i, 0);
+      for (int pz = lane; pz < h.n_split; pz += WARP_N) {
+        int a = ld_ro(h.spL_ord + pz);
+        int s = ld_ro(h.sp_tgt + a), sr = ld_ro(h.sp_r + a);
+        double v[NCH];
+        for (int ch = 0; ch < NCH; ++ch) v[ch] = 0.;
+        for (int tt = 0; tt < nk; ++tt) {
+          int d2 = w.kbuf[tt];
+          double sib = t.a2[cidx(q, i + d2, d2 - d) + sr];
+          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBl[ch * t.bch + rb + (size_t)d2 * S + s] * sib;
+        }
+        for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+      }
+      w_sync();
+      for (int s = lane; s < S; s += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) {
+          double x = seg_sum(w.partA + ch * NM, h.spL_off, s);
+          CB(ch, PL_1, s) = x;
+          CB(ch, PL_B, s) = x + (gM ? CB(ch, PL_M, s) : 0.);
+        }
+      w_sync();
+    }
+    // ---- 2(i,j,sr): right child of B(i',j,s) with left sibling 1(i',i,sl); 1(i,j,sr); parent 2(i,j+1,sp) emitting x[j]
+    {
+      int nk = 0;
+      const unsigned* rj = c.lfr + j * q.mw;
+      int dmax = W < j ? W : j;
+      for (int d20 = d; d20 <= dmax; d20 += WARP_N) {
+        int d2 = d20 + lane;
+        bool ok = d2 <= dmax && row_bit(rj, d2) && row_bit(q.lf + (j - d2) * q.mw, d2 - d);
+        unsigned bal = w_ballot(ok);
+        if (ok) w.kbuf[nk + w_popc(bal & lanemask_lt())] = d2;
+        nk += w_popc(bal);
+      }
+      w_sync();
+      const size_t rb = cidx(q, j, 0);
+      for (int pz = lane; pz < h.n_split; pz += WARP_N) {
+        int a = ld_ro(h.spR_ord + pz);
+        int s = ld_ro(h.sp_tgt + a), sl = ld_ro(h.sp_l + a);
+        double v[NCH];
+        for (int ch = 0; ch < NCH; ++ch) v[ch] = 0.;
+        for (int tt = 0; tt < nk; ++tt) {
+          int d2 = w.kbuf[tt];
+          double sib = t.a1[cidx(q, j - d2, d2 - d) + sl];
+          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBr[ch * t.bch + rb + (size_t)d2 * S + s] * sib;
+        }
+        for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+      }
+      w_sync();
+      for (int s = lane; s < S; s += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_2, s) = seg_sum(w.partA + ch * NM, h.spR_off, s) + CB(ch, PL_1, s);
+      w_sync();
+      if (ok_B(q, i, d + 1)) {
+        const int xr = q.x[j];
+        const double wsr = c.wsf[j];
+        const size_t pb = cidx(q, i, d + 1);
+        for (int pz = lane; pz < h.n_right; pz += WARP_N) {
+          int a = ld_ro(h.rT_ord + pz);
+          int sp = ld_ro(h.r_tgt + a), s1 = ld_ro(h.r_src + a);
+          double wt = ld_ro(p.r_w + a * 5 + xr);
+          if (ld_ro(h.r_flag + a) & 1) wt *= wsr;
+          double ac = cA[PL_2 * S + s1];
+          for (int ch = 0; ch < NCH; ++ch) {
+            double contrib = t.b2[ch * t.bch + pb + sp] * wt;
+            w.partA[ch * NM + pz] = contrib;
+            if (!p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
+          }
+        }
+        w_sync();
+        for (int s = lane; s < S; s += WARP_N)
+          for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_2, s) += seg_sum(w.partA + ch * NM, h.rT_off, s);
+        w_sync();
+      }
+    }
+  }
+  // ---- P(i,j,s1)
+  if (gP) {
+    // 2(i,j,s) <- P(i,j,s)
+    if (gB) {
+      bool c2P = true;
+      double tsc = 0., f0 = 1., f1 = 1.;
+      if (!ne) {
+        tsc = e_sum_ext_m(c.en, q, i, j - 1, false) + c.en.mlintern;
+        c2P = tsc > NINF;
+        if (c2P) { f0 = exp(p.lambda0 * tsc); f1 = exp(p.lambda1 * tsc); }
+      }
+      if (c2P)
+        for (int s = lane; s < S; s += WARP_N) {
+          int sl = ld_ro(h.slot + s);
+          for (int ch = 0; ch < NCH; ++ch) {
+            double y = CB(ch, PL_2, s) * (sl ? f1 : f0);
+            CB(ch, PL_P, s) += y;
+            eh.add(ch, sl, tsc * y * cA[PL_P * S + s]);
+          }
+        }
+      w_sync();
+    }
+    // parent P(i-1,j+1,s) stacking on this pair
+    if (ok_P(q, i - 1, d + 2)) {
+      bool cPP = true;
+      double tsc = 0., f0 = 1., f1 = 1.;
+      if (!ne) {
+        tsc = e_loop(c.en, q, i - 1, j, i, j - 1);
+        cPP = tsc > NINF;
+        if (cPP) { f0 = exp(p.lambda0 * tsc); f1 = exp(p.lambda1 * tsc); }
+      }
+      if (cPP) {
+        const int xl = q.x[i - 1], xr = q.x[j];
+        const double wsl = c.wsf[i - 1], wsr = c.wsf[j];
+        const size_t pb = cidx(q, i - 1, d + 2);
+        for (int pz = lane; pz < h.n_pair; pz += WARP_N) {
+          int a = ld_ro(h.pT_ord + pz);
+          int s = ld_ro(h.p_tgt + a), s1 = ld_ro(h.p_src + a), fl = ld_ro(h.p_flag + a);
+          int sl = ld_ro(h.slot + s);
+          double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr) * (sl ? f1 : f0);
+          if (fl & 1) wt *= wsl;
+          if (fl & 2) wt *= wsr;
+          double ac = cA[PL_P * S + s1];
+          for (int ch = 0; ch < NCH; ++ch) {
+            double contrib = t.bP[ch * t.bch + pb + s] * wt;
+            w.partA[ch * NM + pz] = contrib;
+            double post = contrib * ac;
+            eh.add(ch, sl, tsc * post);
+            if (!p.no_prf && post != 0.) sm_add(w.pcnt + (ch * h.n_pair + a) * 25 + xl * 5 + xr, post);
+          }
+        }
+        w_sync();
+        for (int s = lane; s < S; s += WARP_N)
+          for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_P, s) += seg_sum(w.partA + ch * NM, h.pT_off, s);
+        w_sync();
+      }
+    }
+    // exterior parent O(j,s) <- O(i,sl) P(i,j,sr)
+    {
+      bool cX = true;
+      double tsc = 0., f0 = 1., f1 = 1.;
+      if (!ne) {
+        tsc = e_sum_ext_m(c.en, q, i, j - 1, true);
+        cX = tsc > NINF;
+        if (cX) { f0 = exp(p.lambda0 * tsc); f1 = exp(p.lambda1 * tsc); }
+      }
+      if (cX) {
+        for (int pz = lane; pz < h.n_split; pz += WARP_N) {
+          int a = ld_ro(h.spR_ord + pz);
+          int s = ld_ro(h.sp_tgt + a), sl_ = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
+          int sl = ld_ro(h.slot + s);
+          double term = t.aO[(size_t)i * S + sl_] * (sl ? f1 : f0);
+          double ac = cA[PL_P * S + sr];
+          for (int ch = 0; ch < NCH; ++ch) {
+            double contrib = t.bO[ch * t.boch + (size_t)j * S + s] * term;
+            w.partA[ch * NM + pz] = contrib;
+            eh.add(ch, sl, tsc * contrib * ac);
+          }
+        }
+        w_sync();
+        for (int s = lane; s < S; s += WARP_N)
+          for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_P, s) += seg_sum(w.partA + ch * NM, h.spR_off, s);
+        w_sync();
+      }
+    }
+    // enclosing interior loops E(i',j',s) <- P(i,j,s1) L(i',i,s2) L(j,j',s3)
+    if (h.n_quad > 0) {
+      for (int a = lane; a < h.n_quad; a += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) { w.partA[ch * NM + a] = 0.; w.partT[ch * NM + a] = 0.; }
+      w_sync();
+      walk_outer(c, i, d, w, [&](int n) {
+        for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
+          int a = ld_ro(h.qP_ord + pz);
+          int s = ld_ro(h.q_tgt + a), s2 = ld_ro(h.q_s2 + a), s3 = ld_ro(h.q_s3 + a);
+          const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
+          double v[NCH], vt[NCH];
+          for (int ch = 0; ch < NCH; ++ch) { v[ch] = w.partA[ch * NM + pz]; vt[ch] = w.partT[ch * NM + pz]; }
+          for (int pp = 0; pp < n; ++pp) {
+            int i2 = w.bi[pp], j2 = w.bj[pp];
+            double term = t.aLl[cidx(q, i2, i - i2) + s2] * t.aLr[cidx(q, j2, j2 - j) + s3] * bf[pp];
+            double tsc = w.bt[pp];
+            size_t eb = cidx(q, i2, j2 - i2) + s;
+            for (int ch = 0; ch < NCH; ++ch) {
+              double x = t.bEl[ch * t.bch + eb] * term;
+              v[ch] += x;
+              vt[ch] += tsc * x;
+            }
+          }
+          for (int ch = 0; ch < NCH; ++ch) { w.partA[ch * NM + pz] = v[ch]; w.partT[ch * NM + pz] = vt[ch]; }
+        }
+      });
+      for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
+        int a = ld_ro(h.qP_ord + pz);
+        int sl = ld_ro(h.slot + ld_ro(h.q_tgt + a));
+        double ac = cA[PL_P * S + ld_ro(h.q_s1 + a)];
+        for (int ch = 0; ch < NCH; ++ch) eh.add(ch, sl, w.partT[ch * NM + pz] * ac);
+      }
+      for (int s = lane; s < S; s += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_P, s) += seg_sum(w.partA + ch * NM, h.qP_off, s);
+      w_sync();
+    }
+  }
+  // ---- L(i,j,s)
+  {
+    // hairpin closed by (i-1,j): E(i,j,s) <- L(i,j,s)
+    if (gE) {
+      bool cH = true;
+      double tH = 0., h0 = 1., h1 = 1.;
+      if (!ne) {
+        tH = e_hairpin(c.en, q, i - 1, j);
+        cH = tH > NINF;
+        if (cH) { h0 = exp(p.lambda0 * tH); h1 = exp(p.lambda1 * tH); }
+      }
+      if (cH)
+        for (int s = lane; s < S; s += WARP_N) {
+          if (!ld_ro(h.is_loop + s)) continue;
+          int sl = ld_ro(h.slot + s);
+          for (int ch = 0; ch < NCH; ++ch) {
+            double y = CB(ch, PL_E, s) * (sl ? h1 : h0);
+            CB(ch, PL_L, s) += y;
+            eh.add(ch, sl, tH * y * cA[PL_L * S + s]);
+          }
+        }
+      w_sync();
+    }
+    // parent L(i,j+1,sp) emitting x[j]
+    if (d + 1 <= W && j + 1 <= L) {
+      const int xr = q.x[j];
+      const double wsr = c.wsf[j];
+      const size_t pb = cidx(q, i, d + 1);
+      for (int pz = lane; pz < h.n_right; pz += WARP_N) {
+        int a = ld_ro(h.rT_ord + pz);
+        int fl = ld_ro(h.r_flag + a);
+        double contrib0 = 0.;
+        int sp = ld_ro(h.r_tgt + a), s1 = ld_ro(h.r_src + a);
+        double wt = 0.;
+        if (fl & 2) {
+          wt = ld_ro(p.r_w + a * 5 + xr);
+          if (fl & 1) wt *= wsr;
+        }
+        double ac = cA[PL_L * S + s1];
+        for (int ch = 0; ch < NCH; ++ch) {
+          double contrib = (fl & 2) ? t.bL[ch * t.bch + pb + sp] * wt : contrib0;
+          w.partA[ch * NM + pz] = contrib;
+          if (!p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
+        }
+      }
+      w_sync();
+      for (int s = lane; s < S; s += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_L, s) += seg_sum(w.partA + ch * NM, h.rT_off, s);
+      w_sync();
+    }
+    // unpaired flanks of interior loops
+    if (d >= 1 && d <= c.Ceff && h.n_quad > 0) {
+      if (i >= 1) {
+        for (int a = lane; a < h.n_quad; a += WARP_N)
+          for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
+        w_sync();
+        const size_t eb = cidx(q, i, 0);
+        walk_left_flank(c, i, d, w, [&](int n) {
+          for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
+            int a = ld_ro(h.qL_ord + pz);
+            int s = ld_ro(h.q_tgt + a), s1 = ld_ro(h.q_s1 + a), s3 = ld_ro(h.q_s3 + a);
+            const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
+            double v[NCH];
+            for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
+            for (int pp = 0; pp < n; ++pp) {
+              int l = w.bi[pp], j2 = w.bj[pp];
+              double term = t.aP[cidx(q, l, l - j) + s1] * t.aLr[cidx(q, j2, j2 - l) + s3] * bf[pp];
+              for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEl[ch * t.bch + eb + (size_t)(j2 - i) * S + s] * term;
+            }
+            for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+          }
+        });
+        for (int s = lane; s < S; s += WARP_N)
+          for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_L, s) += seg_sum(w.partA + ch * NM, h.qL_off, s);
+        w_sync();
+      }
+      if (j + 1 <= L) {
+        for (int a = lane; a < h.n_quad; a += WARP_N)
+          for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
+        w_sync();
+        const size_t eb = cidx(q, j, 0);
+        walk_right_flank(c, i, d, w, [&](int n) {
+          for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
+            int a = ld_ro(h.qR_ord + pz);
+            int s = ld_ro(h.q_tgt + a), s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a);
+            const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
+            double v[NCH];
+            for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
+            for (int pp = 0; pp < n; ++pp) {
+              int k = w.bi[pp], i2 = w.bj[pp];
+              double term = t.aP[cidx(q, i, i - k) + s1] * t.aLl[cidx(q, i2, k - i2) + s2] * bf[pp];
+              for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEr[ch * t.bch + eb + (size_t)(j - i2) * S + s] * term;
+            }
+            for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+          }
+        });
+        for (int s = lane; s < S; s += WARP_N)
+          for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_L, s) += seg_sum(w.partA + ch * NM, h.qR_off, s);
+        w_sync();
+      }
+    }
+  }
+  // ---- write back
+  for (int s = lane; s < S; s += WARP_N)
+    for (int ch = 0; ch < NCH; ++ch) {
+      const size_t o = ch * t.bch;
+      if (d >= 1) t.bL[o + il + s] = CB(ch, PL_L, s);
+      if (gP) t.bP[o + il + s] = CB(ch, PL_P, s);
+      if (gE) { t.bEl[o + il + s] = CB(ch, PL_E, s); t.bEr[o + ir + s] = CB(ch, PL_E, s); }
+      if (gM) t.bM[o + il + s] = CB(ch, PL_M, s);
+      if (gB) { t.bBl[o + il + s] = CB(ch, PL_B, s); t.bBr[o + ir + s] = CB(ch, PL_B, s); t.b2[o + il + s] = CB(ch, PL_2, s); }
+    }
+  w_sync();
+#undef CB
+}
+
+}  // namespace lin
+}  // namespace relem
+#endif

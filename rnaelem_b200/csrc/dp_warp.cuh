@@ -13,43 +13,10 @@
 #ifndef RELEM_DP_WARP_CUH
 #define RELEM_DP_WARP_CUH
 #include "dp_pass.cuh"
+#include "dp_prim.cuh"
 
 namespace relem {
 namespace dp {
-
-#ifdef RELEM_HOST_EMU
-#define WARP_N 1
-RDEV int lane_id() { return 0; }
-RDEV int warp_id() { return 0; }
-RDEV int n_warps() { return 1; }
-RDEV unsigned w_ballot(bool p) { return p ? 1u : 0u; }
-RDEV double w_shfl_down(double v, int) { return v; }
-RDEV int w_shfl_down(int v, int) { return v; }
-RDEV int w_shfl_up(int v, int) { return v; }
-RDEV double w_shfl(double v, int) { return v; }
-RDEV int w_shfl(int v, int) { return v; }
-RDEV void w_sync() {}
-RDEV void w_fence() {}
-RDEV int w_ffs(unsigned b) { return __builtin_ffs((int)b); }
-RDEV void sm_add(double* p, double v) { *p += v; }
-RDEV int ctr_next(int* c) { return (*c)++; }
-#else
-#define WARP_N 32
-RDEV int lane_id() { return (int)(threadIdx.x & 31); }
-RDEV int warp_id() { return (int)(threadIdx.x >> 5); }
-RDEV int n_warps() { return (int)(blockDim.x >> 5); }
-RDEV unsigned w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
-RDEV double w_shfl_down(double v, int o) { return __shfl_down_sync(0xFFFFFFFFu, v, o); }
-RDEV int w_shfl_down(int v, int o) { return __shfl_down_sync(0xFFFFFFFFu, v, o); }
-RDEV int w_shfl_up(int v, int o) { return __shfl_up_sync(0xFFFFFFFFu, v, o); }
-RDEV double w_shfl(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
-RDEV int w_shfl(int v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
-RDEV void w_sync() { __syncwarp(); }
-RDEV void w_fence() { __threadfence(); }
-RDEV int w_ffs(unsigned b) { return __ffs((int)b); }
-RDEV void sm_add(double* p, double v) { atomicAdd(p, v); }
-RDEV int ctr_next(int* c) { return atomicAdd(c, 1); }
-#endif
 
 RDEV void lse_merge(Lse& a, double m2, double s2) {
   if (!(m2 > NINF)) return;

@@ -1,0 +1,38 @@
+// lin_api.hpp -- host-side interface between relem_api.cu (the C ABI) and relem_lin.cu (the scaled linear-space
+// E-step kernels, dp_lin.cuh).  relem_lin.cu is its own translation unit so that it can be compiled with FMA
+// contraction on, while the Viterbi code of relem_api.cu keeps -fmad=false.
+#ifndef RELEM_LIN_API_HPP
+#define RELEM_LIN_API_HPP
+#include <string>
+
+#include "dp_batch.hpp"
+#include "dp_common.cuh"
+#include "lin_model.hpp"
+
+namespace relem {
+namespace lin {
+
+struct LinState;  // owns the per-slot scratch of the linear-space kernels
+LinState* lin_state_create();
+void lin_state_destroy(LinState*);
+
+struct LinLaunch {
+  LinHMM h;
+  LinParams p;
+  dp::DevEnergy en, el;
+  double kappa0;          // per-base scale of the energy-only filter pass
+  dp::BatchView b;
+  int Lmax, max_span;
+  dp::EstepOut out;       // NCH = 1: ENo receives ENo-ENx and ENx zeros (likewise EH)
+  unsigned char* flag;    // [nseq] device: 1 = sequence left the fp64 range, re-run it on the log-space path
+  int nch;                // 1 = difference only, 2 = both boundary conditions
+  int sm_count;
+  void* stream;           // cudaStream_t
+  int max_slots;          // 0 = no limit
+};
+// returns 0 on success; on failure err holds the message.  launches = kernels launched.
+int lin_estep_launch(LinState*, const LinLaunch&, float* kernel_ms, int* launches, std::string& err);
+
+}  // namespace lin
+}  // namespace relem
+#endif

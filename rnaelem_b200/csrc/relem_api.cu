@@ -20,6 +20,7 @@
 
 #include "dp_layout.hpp"
 #include "host_model.hpp"
+#include "lin_api.hpp"
 
 #ifndef RELEM_HOST_EMU
 #include <cuda_runtime.h>
@@ -104,6 +105,13 @@ struct relem_ctx {
   DevBuf d_scratch, d_queue, d_res, d_Z, d_ENo, d_ENx, d_EH, d_eff, d_skip;
   DevBuf d_s1, d_s2, d_s3, d_s4, d_s5, d_s6, d_s7, d_s8, d_s9, d_s10;
   DevEnergy den;
+  DevEnergy denl;                      // exponentiated copy of the energy tables (linear-space filter pass)
+  lin::LinHost linh;                   // transition lists grouped by parent and by child
+  lin::LinHMM dlh;
+  lin::LinParams dlp;
+  lin::LinState* lin = nullptr;
+  DevBuf d_energy_lin, d_lin_ints, d_lin_w, d_flag, d_order2;
+  bool have_lin = false;
   DevHMM dh, dnull;
   DevParams dpar, dnullpar;
   std::vector<TimingEntry> timing;
@@ -193,6 +201,19 @@ bool upload_energy(relem_ctx* c) {
   e.no_ene = c->no_ene; e.max_span = c->max_span; e.max_iloop = c->max_iloop;
   e.filter = c->min_bpp != 0. ? 1 : 0;
   e.min_lnbpp = std::log(c->min_bpp);
+  // the same tables as Boltzmann factors (exp of the log weights; forbidden = 0)
+  std::vector<double> lblob(blob.size());
+  for (size_t k = 0; k < blob.size(); ++k) lblob[k] = std::exp(blob[k]);
+  if (!upload(c->d_energy_lin, lblob)) return false;
+  DevEnergy& l = c->denl;
+  l = e;
+  const double* lb = c->d_energy_lin.as<double>();
+  l.hairpin_len = lb + o_hl; l.mismatch_h = lb + o_mmh; l.mismatch_i = lb + o_mmi; l.mismatch_m = lb + o_mmm;
+  l.mismatch_1ni = lb + o_1ni; l.mismatch_23i = lb + o_23i; l.mismatch_ext = lb + o_ext; l.stack = lb + o_st;
+  l.bulge = lb + o_bu; l.internal = lb + o_in; l.ninio = lb + o_ni; l.dangle5 = lb + o_d5; l.dangle3 = lb + o_d3;
+  l.int11 = lb + o_11; l.int21 = lb + o_21; l.int22 = lb + o_22;
+  l.term_au = std::exp(t.term_au); l.mlintern = std::exp(t.mlintern); l.mlclosing = std::exp(t.mlclosing);
+  l.tri_w = lb + o_w3; l.tetra_w = lb + o_w4; l.hexa_w = lb + o_w6;
   return true;
 }
 
@@ -226,7 +247,8 @@ struct Launch {
 };
 
 // choose the number of resident CTAs (= scratch slots) and make sure the scratch fits
-int plan_launch(relem_ctx* c, const relem_batch* b, int nch, bool coupled, const void* kernel, Launch& L) {
+int plan_launch(relem_ctx* c, const relem_batch* b, int nch, bool coupled, const void* kernel, Launch& L,
+                int max_n = 1 << 30) {
   int S = c->flat.S, M = c->flat.M;
   L.c = c;
   L.lay = make_layout(std::max(1, b->Lmax), c->max_span, S, M, c->n_theta, nch, coupled);
@@ -246,7 +268,7 @@ int plan_launch(relem_ctx* c, const relem_batch* b, int nch, bool coupled, const
   size_t avail = free_b + c->d_scratch.bytes;
   size_t per = L.lay.stride * sizeof(double);
   long long by_mem = (long long)((avail * 0.85) / (double)per);
-  L.nslots = (int)std::min<long long>(std::min<long long>(b->nseq, (long long)c->sm_count * occ), by_mem);
+  L.nslots = (int)std::min<long long>(std::min<long long>(std::min(b->nseq, max_n), (long long)c->sm_count * occ), by_mem);
   if (const char* e = std::getenv("RELEM_MAX_SLOTS")) L.nslots = std::min(L.nslots, std::max(1, std::atoi(e)));
   if (L.nslots < 1) return fail(c, RELEM_ENOMEM, "not enough device memory for one sequence slot");
 #endif
@@ -352,7 +374,8 @@ void relem_destroy(relem_ctx* c) {
   }
   c->d_coll.release();
 #endif
-  DevBuf* all[] = {&c->d_prof, &c->d_energy, &c->d_codes, &c->d_hmm, &c->d_null, &c->d_n2s, &c->d_theta, &c->d_null_theta,
+  if (c->lin) lin::lin_state_destroy(c->lin);
+  DevBuf* all[] = {&c->d_energy_lin, &c->d_lin_ints, &c->d_lin_w, &c->d_flag, &c->d_order2, &c->d_prof, &c->d_energy, &c->d_codes, &c->d_hmm, &c->d_null, &c->d_n2s, &c->d_theta, &c->d_null_theta,
                    &c->d_scratch, &c->d_queue, &c->d_res, &c->d_Z, &c->d_ENo, &c->d_ENx, &c->d_EH, &c->d_eff,
                    &c->d_skip, &c->d_s1, &c->d_s2, &c->d_s3, &c->d_s4, &c->d_s5, &c->d_s6, &c->d_s7, &c->d_s8,
                    &c->d_s9, &c->d_s10};
@@ -402,6 +425,9 @@ int relem_set_pattern(relem_ctx* c, const char* pattern, int no_rss, int no_prf)
   if (!upload_hmm(c->flat, c->d_hmm, c->dh) || !upload(c->d_n2s, n2s) ||
       !c->d_theta.reserve(sizeof(double) * c->n_theta))
     return fail(c, RELEM_ENOMEM, "automaton upload failed");
+  c->linh.build(c->flat);
+  if (!upload(c->d_lin_ints, c->linh.blob)) return fail(c, RELEM_ENOMEM, "automaton upload failed");
+  c->linh.view(c->d_lin_ints.as<int>(), c->dlh);
   c->have_pattern = true;
   c->have_params = false;
   return RELEM_OK;
@@ -479,6 +505,26 @@ int relem_set_params(relem_ctx* c, const double* theta_flat, int n_theta, const 
   if (!Dev::h2d(c->d_theta.p, theta_flat, sizeof(double) * n_theta)) return fail(c, RELEM_ECUDA, "theta upload failed");
   c->dpar.theta = c->d_theta.as<double>(); c->dpar.n_theta = n_theta;
   c->dpar.lambda0 = lambda[0]; c->dpar.lambda1 = lambda[1]; c->dpar.ltau = std::log(tau); c->dpar.no_prf = c->no_prf;
+  {
+    // linear-space tables: per-base scale kappa = exp(-mean background log emission), so that background
+    // emissions are O(1) factors
+    double lk = 0.;
+    if (!c->no_prf && !c->hmm.row_size.empty()) {
+      double m = 0.;
+      int r0 = c->hmm.row_size[0], cnt = 0;
+      for (int k = 0; k < r0; ++k) if (std::isfinite(theta_flat[k])) { m += theta_flat[k]; ++cnt; }
+      if (cnt) lk = -m / cnt;
+    }
+    std::vector<double> wb;
+    size_t o_r, o_l, o_p;
+    lin::build_lin_weights(c->flat, theta_flat, tau, c->no_prf, std::exp(lk), wb, o_r, o_l, o_p);
+    if (!upload(c->d_lin_w, wb)) return fail(c, RELEM_ENOMEM, "weight upload failed");
+    const double* b = c->d_lin_w.as<double>();
+    c->dlp.r_w = b + o_r; c->dlp.l_w = b + o_l; c->dlp.p_w = b + o_p;
+    c->dlp.lambda0 = lambda[0]; c->dlp.lambda1 = lambda[1]; c->dlp.kappa = std::exp(lk); c->dlp.ln_kappa = lk;
+    c->dlp.no_prf = c->no_prf; c->dlp.n_theta = n_theta;
+    c->have_lin = true;
+  }
   c->have_params = true;
   return RELEM_OK;
 }
@@ -546,13 +592,6 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
 #ifndef RELEM_HOST_EMU
   CUDA_TRY(c, cudaSetDevice(c->dev));
 #endif
-  Launch L;
-#ifdef RELEM_HOST_EMU
-  rc = plan_launch(c, b, 2, true, nullptr, L);
-#else
-  rc = plan_launch(c, b, 2, true, (const void*)relem_estep_kernel, L);
-#endif
-  if (rc) return rc;
   int nres = 7 + 2 * NT;
   if (!c->d_Z.reserve(sizeof(double) * 3 * nseq) || !c->d_ENo.reserve(sizeof(double) * (size_t)NT * nseq) ||
       !c->d_ENx.reserve(sizeof(double) * (size_t)NT * nseq) || !c->d_EH.reserve(sizeof(double) * 4 * nseq) ||
@@ -567,18 +606,62 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
   ModelView nullm, m;
   model_views(c, nullm, m);
   BatchView bv = batch_view(b);
-  {
+  // Throughput path: scaled linear-space kernels (relem_lin.cu).  Sequences whose scaled values leave the fp64
+  // range come back flagged and are re-run below on the log-space kernel, which also serves RELEM_PATH=log.
+  const char* path_env = std::getenv("RELEM_PATH");
+  bool use_lin = c->have_lin && !(path_env && std::strcmp(path_env, "log") == 0);
+  int n_fallback = nseq;
+  if (use_lin) {
+    if (!c->lin) c->lin = lin::lin_state_create();
+    if (!c->d_flag.reserve(nseq) || !Dev::zero(c->d_flag.p, nseq)) return fail(c, RELEM_ENOMEM, "flag allocation failed");
+    lin::LinLaunch ll;
+    ll.h = c->dlh; ll.p = c->dlp; ll.en = c->den; ll.el = c->denl;
+    ll.kappa0 = std::exp(-0.3);
+    ll.b = bv; ll.Lmax = b->Lmax; ll.max_span = c->max_span; ll.out = eo;
+    ll.flag = c->d_flag.as<unsigned char>();
+    ll.nch = (out->ENo || out->ENx || out->EH) ? 2 : 1;
+    ll.max_slots = 0;
+    if (const char* e = std::getenv("RELEM_MAX_SLOTS")) ll.max_slots = std::max(1, std::atoi(e));
+#ifndef RELEM_HOST_EMU
+    ll.sm_count = c->sm_count; ll.stream = (void*)c->stream;
+#else
+    ll.sm_count = 1; ll.stream = nullptr;
+#endif
+    float ms = 0.f; int nl = 0; std::string lerr;
+    int lrc = lin::lin_estep_launch(c->lin, ll, &ms, &nl, lerr);
+    if (lrc) return fail(c, lrc == 3 ? RELEM_ENOMEM : RELEM_ECUDA, "linear-space E-step: " + lerr);
+    c->timing.push_back(TimingEntry{"relem_estep_lin_kernel", ms, nl});
+    std::vector<unsigned char> flags(nseq);
+    if (!Dev::d2h(flags.data(), c->d_flag.p, nseq)) return fail(c, RELEM_ECUDA, "flag copy failed");
+    std::vector<int> redo;
+    for (int k = 0; k < nseq; ++k) if (flags[k]) redo.push_back(k);
+    n_fallback = (int)redo.size();
+    if (n_fallback) {
+      if (!upload(c->d_order2, redo)) return fail(c, RELEM_ENOMEM, "fallback list upload failed");
+      bv.order = c->d_order2.as<int>();
+      bv.nseq = n_fallback;
+    }
+  }
+  if (n_fallback > 0) {
+    Launch L;
+#ifdef RELEM_HOST_EMU
+    rc = plan_launch(c, b, 2, true, nullptr, L, n_fallback);
+#else
+    rc = plan_launch(c, b, 2, true, (const void*)relem_estep_kernel, L, n_fallback);
+#endif
+    if (rc) return rc;
     Timer t(c, "relem_estep_kernel");
 #ifdef RELEM_HOST_EMU
     std::vector<unsigned char> smem(L.lay.sm_total + 64);
     relem_estep_kernel(nullm, m, bv, L.lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), eo, smem.data());
 #else
-    relem_estep_kernel<<<L.nslots, RELEM_CTA_THREADS, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
-                                                                      c->d_queue.as<int>(), eo);
+    relem_estep_kernel<<<L.nslots, RELEM_CTA_THREADS, L.lay.sm_total, c->stream>>>(
+        nullm, m, bv, L.lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), eo);
     CUDA_TRY(c, cudaGetLastError());
 #endif
     t.stop();
   }
+  bv = batch_view(b);
   {
     Timer t(c, "relem_reduce_kernel");
 #ifdef RELEM_HOST_EMU
