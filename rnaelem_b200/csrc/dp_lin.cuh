@@ -42,22 +42,36 @@ struct LinEnergyScalars {  // linear-domain copies of the scalar energy terms
   double term_au, mlintern, mlclosing;
 };
 
-struct LinCtx {
+// model-wide data: __constant__ on the device (uploaded once per launch), so that the out-of-line energy
+// functions below reach it without arguments
+struct LinConst {
   LinHMM h;
   LinParams p;
   DevEnergy en;  // log-Boltzmann tables (coupled passes: exp(lambda * tsc), and tsc itself for the lambda gradient)
   DevEnergy el;  // the same tables exponentiated (energy-only filter pass, lambda = 1)
+  double k0, k0sq;  // per-base scale of the energy-only pass
+};
+#ifdef RELEM_HOST_EMU
+static LinConst LC;
+#define LIN_NOINLINE __attribute__((noinline))
+#else
+__constant__ LinConst LC;
+#define LIN_NOINLINE __device__ __noinline__
+#endif
+
+// per-sequence view, one copy per CTA in shared memory
+struct LinCtx {
   SeqView q;     // x, special hairpins, bp (by left end), lf (by left end), sizes
   const unsigned* bpr;  // bp by right end: bit d of row j <-> pair (j-d, j)
   const unsigned* lfr;  // left_bp_ok by right end
   const double* wsf;    // exp(position weight) [L]
   const double* k0pow;  // kappa0^u, u = 0..W+1
-  double k0, k0sq;
   int Ceff;             // min(C, 30): loops longer than 30 have zero weight (energy_param.hpp:754-755)
 };
 
-RDEV size_t cidx(const SeqView& q, int row, int d) { return ((size_t)row * (size_t)q.W1 + (size_t)d) * (size_t)q.S; }
-RDEV size_t kidx(const SeqView& q, int row, int d) { return (size_t)row * (size_t)q.W1 + (size_t)d; }
+// flat offsets (one band table of one sequence has < 2^31 entries: checked by the host)
+RDEV unsigned cidx(const SeqView& q, int row, int d) { return (unsigned)((row * q.W1 + d) * q.S); }
+RDEV unsigned kidx(const SeqView& q, int row, int d) { return (unsigned)(row * q.W1 + d); }
 
 // n (1..32) mask bits of a row starting at bit lo; bits beyond the row read as 0
 RDEV unsigned win_bits(const unsigned* row, int mw, int lo, int n) {
@@ -135,6 +149,23 @@ RDEV double l_loop(const DevEnergy& el, const SeqView& sq, int i, int j, int p, 
          ld_ro(mm + (type2 * 5 + x[q + 1]) * 5 + x[p - 1]);
 }
 
+// Out-of-line copies: the case analysis above is ~100 instructions and is needed in a dozen places; keeping one
+// copy each keeps the kernels inside the instruction cache.
+LIN_NOINLINE double nl_l_loop(const SeqView* q, int i, int j, int p, int qq) { return l_loop(LC.el, *q, i, j, p, qq); }
+LIN_NOINLINE double nl_l_ext(const SeqView* q, int i, int j, int ext) { return l_sum_ext_m(LC.el, *q, i, j, ext != 0); }
+LIN_NOINLINE double nl_l_hairpin(const SeqView* q, int i, int j) { return l_hairpin(LC.el, *q, i, j); }
+LIN_NOINLINE double nl_e_loop(const SeqView* q, int i, int j, int p, int qq) { return e_loop(LC.en, *q, i, j, p, qq); }
+LIN_NOINLINE double nl_e_ext(const SeqView* q, int i, int j, int ext) { return e_sum_ext_m(LC.en, *q, i, j, ext != 0); }
+LIN_NOINLINE double nl_e_hairpin(const SeqView* q, int i, int j) { return e_hairpin(LC.en, *q, i, j); }
+struct F2 { double f0, f1; };
+// Boltzmann factors of a transition energy for the two lambda slots
+LIN_NOINLINE F2 boltz2(double tsc) {
+  F2 r;
+  r.f0 = exp(LC.p.lambda0 * tsc);
+  r.f1 = exp(LC.p.lambda1 * tsc);
+  return r;
+}
+
 // ================================================================================= energy-only filter (K0)
 // Tables of the energy-only grammar (one motif state, no emissions): EnergyModel::calc_BPP (energy_model.hpp:188-193).
 // a: P (by right end), E, M, 1 (by left end), 2 (by right end); b: P, E, M, B (both orientations), 2.  L == 1.
@@ -145,7 +176,7 @@ struct K0Tabs {
 
 RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
   const SeqView& q = c.q;
-  const DevEnergy& el = c.el;
+  const DevEnergy& el = LC.el;
   const int j = i + d, lane = lane_id();
   const bool ne = el.no_ene != 0;
   const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
@@ -153,8 +184,8 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
   double vP = 0.;
   if (gP) {
     if (ok_E(q, i + 1, d - 2)) vP += t.E[kidx(q, i + 1, d - 2)];
-    if (ok_P(q, i + 1, d - 2)) vP += t.P[kidx(q, j - 1, d - 2)] * (ne ? 1. : l_loop(el, q, i, j - 1, i + 1, j - 2));
-    vP *= c.k0sq;
+    if (ok_P(q, i + 1, d - 2)) vP += t.P[kidx(q, j - 1, d - 2)] * (ne ? 1. : nl_l_loop(&q, i, j - 1, i + 1, j - 2));
+    vP *= LC.k0sq;
   }
   double vB = 0.;
   if (gB) {
@@ -168,13 +199,13 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
   }
   double v2 = 0., v1 = 0.;
   if (gB) {
-    if (ok_B(q, i, d - 1)) v2 += t.o2[kidx(q, j - 1, d - 1)] * c.k0;
-    if (gP) v2 += vP * (ne ? 1. : l_sum_ext_m(el, q, i, j - 1, false) * el.mlintern);
+    if (ok_B(q, i, d - 1)) v2 += t.o2[kidx(q, j - 1, d - 1)] * LC.k0;
+    if (gP) v2 += vP * (ne ? 1. : nl_l_ext(&q, i, j - 1, 0) * el.mlintern);
     v1 = v2 + vB;
   }
   double vM = 0.;
   if (gM) {
-    if (ok_M(q, i + 1, d - 1)) vM += t.M[kidx(q, i + 1, d - 1)] * c.k0;
+    if (ok_M(q, i + 1, d - 1)) vM += t.M[kidx(q, i + 1, d - 1)] * LC.k0;
     if (gB) vM += vB;
   }
   double vE = 0.;
@@ -193,12 +224,12 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
         int b = w_ffs(m) - 1;
         m &= m - 1;
         int dd = lo + b, l = k + dd, u2 = d - u1 - dd;
-        acc += t.P[kidx(q, l, dd)] * c.k0pow[u1 + u2] * (ne ? 1. : l_loop(el, q, i - 1, j, k, l - 1));
+        acc += t.P[kidx(q, l, dd)] * c.k0pow[u1 + u2] * (ne ? 1. : nl_l_loop(&q, i - 1, j, k, l - 1));
       }
     }
     vE = w_sum(acc);
-    if (gM) vE += vM * (ne ? 1. : l_sum_ext_m(el, q, j, i - 1, false) * (el.mlclosing * el.mlintern));
-    if (d >= 1) vE += c.k0pow[d] * (ne ? 1. : l_hairpin(el, q, i - 1, j));
+    if (gM) vE += vM * (ne ? 1. : nl_l_ext(&q, j, i - 1, 0) * (el.mlclosing * el.mlintern));
+    if (d >= 1) vE += c.k0pow[d] * (ne ? 1. : nl_l_hairpin(&q, i - 1, j));
   }
   if (lane == 0) {
     if (gP) t.P[kidx(q, j, d)] = vP;
@@ -211,7 +242,7 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
 // exterior row, one warp: O(j) = sum_i O(i) P(i,j) ext(i,j-1) + O(j-1)
 RDEV void k0_inside_ext(const LinCtx& c, const K0Tabs& t) {
   const SeqView& q = c.q;
-  const DevEnergy& el = c.el;
+  const DevEnergy& el = LC.el;
   const int L = q.L, lane = lane_id();
   const bool ne = el.no_ene != 0;
   if (lane == 0) t.O[0] = 1.;
@@ -223,16 +254,16 @@ RDEV void k0_inside_ext(const LinCtx& c, const K0Tabs& t) {
     for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
       int u = u0 + lane;
       if (u <= dmax && row_bit(rj, u))
-        acc += t.O[j - u] * t.P[kidx(q, j, u)] * (ne ? 1. : l_sum_ext_m(el, q, j - u, j - 1, true));
+        acc += t.O[j - u] * t.P[kidx(q, j, u)] * (ne ? 1. : nl_l_ext(&q, j - u, j - 1, 1));
     }
     acc = w_sum(acc);
-    if (lane == 0) t.O[j] = acc + t.O[j - 1] * c.k0;
+    if (lane == 0) t.O[j] = acc + t.O[j - 1] * LC.k0;
     w_sync();
   }
 }
 RDEV void k0_outside_ext(const LinCtx& c, const K0Tabs& t, double rootw) {
   const SeqView& q = c.q;
-  const DevEnergy& el = c.el;
+  const DevEnergy& el = LC.el;
   const int L = q.L, lane = lane_id();
   const bool ne = el.no_ene != 0;
   if (lane == 0) t.bO[L] = rootw;
@@ -244,27 +275,27 @@ RDEV void k0_outside_ext(const LinCtx& c, const K0Tabs& t, double rootw) {
     for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
       int u = u0 + lane;
       if (u <= dmax && row_bit(ri, u))
-        acc += t.bO[i + u] * t.P[kidx(q, i + u, u)] * (ne ? 1. : l_sum_ext_m(el, q, i, i + u - 1, true));
+        acc += t.bO[i + u] * t.P[kidx(q, i + u, u)] * (ne ? 1. : nl_l_ext(&q, i, i + u - 1, 1));
     }
     acc = w_sum(acc);
-    if (lane == 0) t.bO[i] = acc + t.bO[i + 1] * c.k0;
+    if (lane == 0) t.bO[i] = acc + t.bO[i + 1] * LC.k0;
     w_sync();
   }
 }
 
 RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
   const SeqView& q = c.q;
-  const DevEnergy& el = c.el;
+  const DevEnergy& el = LC.el;
   const int j = i + d, lane = lane_id(), L = q.L, W = q.W;
   const bool ne = el.no_ene != 0;
   const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
   if (!(gP || gB || gM || gE)) return;
   double bE = 0.;
-  if (gE) bE = t.bP[kidx(q, i - 1, d + 2)] * c.k0sq;
+  if (gE) bE = t.bP[kidx(q, i - 1, d + 2)] * LC.k0sq;
   double bM = 0.;
   if (gM) {
-    if (gE) bM += bE * (ne ? 1. : l_sum_ext_m(el, q, j, i - 1, false) * (el.mlclosing * el.mlintern));
-    if (ok_M(q, i - 1, d + 1)) bM += t.bM[kidx(q, i - 1, d + 1)] * c.k0;
+    if (gE) bM += bE * (ne ? 1. : nl_l_ext(&q, j, i - 1, 0) * (el.mlclosing * el.mlintern));
+    if (ok_M(q, i - 1, d + 1)) bM += t.bM[kidx(q, i - 1, d + 1)] * LC.k0;
   }
   double b1 = 0., bB = 0., b2 = 0.;
   if (gB) {
@@ -289,13 +320,13 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
       }
       b2 = w_sum(b2) + b1;
     }
-    if (ok_B(q, i, d + 1)) b2 += t.b2[kidx(q, i, d + 1)] * c.k0;
+    if (ok_B(q, i, d + 1)) b2 += t.b2[kidx(q, i, d + 1)] * LC.k0;
   }
   double bP = 0.;
   if (gP) {
-    if (gB) bP += b2 * (ne ? 1. : l_sum_ext_m(el, q, i, j - 1, false) * el.mlintern);
-    if (ok_P(q, i - 1, d + 2)) bP += t.bP[kidx(q, i - 1, d + 2)] * c.k0sq * (ne ? 1. : l_loop(el, q, i - 1, j, i, j - 1));
-    bP += t.O[i] * t.bO[j] * (ne ? 1. : l_sum_ext_m(el, q, i, j - 1, true));
+    if (gB) bP += b2 * (ne ? 1. : nl_l_ext(&q, i, j - 1, 0) * el.mlintern);
+    if (ok_P(q, i - 1, d + 2)) bP += t.bP[kidx(q, i - 1, d + 2)] * LC.k0sq * (ne ? 1. : nl_l_loop(&q, i - 1, j, i, j - 1));
+    bP += t.O[i] * t.bO[j] * (ne ? 1. : nl_l_ext(&q, i, j - 1, 1));
     // enclosing pairs: this cell is the inner pair (k=i,l=j) of E(i',j')
     const int C = c.Ceff;
     const int hi = W < d + C + 2 ? W : d + C + 2;
@@ -311,7 +342,7 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
         int u2 = w_ffs(m) - 1;
         m &= m - 1;
         int j2 = j + u2;
-        acc += t.bE[kidx(q, i2, d + u1 + u2)] * c.k0pow[u1 + u2] * (ne ? 1. : l_loop(el, q, i2 - 1, j2, i, j - 1));
+        acc += t.bE[kidx(q, i2, d + u1 + u2)] * c.k0pow[u1 + u2] * (ne ? 1. : nl_l_loop(&q, i2 - 1, j2, i, j - 1));
       }
     }
     bP += w_sum(acc);
@@ -328,7 +359,7 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
 struct CTabs {
   double *aP, *aE, *aM, *a1, *a2, *aLl, *aLr, *aO;          // aP, a2, aLr by right end; the rest by left end
   double *bP, *bEl, *bEr, *bM, *bBl, *bBr, *b2, *bL, *bO;   // bEr, bBr by right end; channel c at + c*bch (bO: + c*boch)
-  size_t bch, boch;
+  unsigned bch, boch;
 };
 
 struct WarpLin {
@@ -383,8 +414,9 @@ RDEV void batch_push(const LinCtx& c, WarpLin& w, int& n, bool ok, int ia, int i
   if (ok) {
     int pos = n + w_popc(bal & lanemask_lt());
     w.bi[pos] = ia; w.bj[pos] = ib; w.bt[pos] = tsc;
-    w.bf0[pos] = exp(c.p.lambda0 * tsc);
-    w.bf1[pos] = exp(c.p.lambda1 * tsc);
+    F2 ff = boltz2(tsc);
+    w.bf0[pos] = ff.f0;
+    w.bf1[pos] = ff.f1;
   }
   n += w_popc(bal);
 }
@@ -417,7 +449,7 @@ template <class F> RDEV void walk_inner(const LinCtx& c, int i, int d, WarpLin& 
       int l = k + lo + b;
       double tsc = 0.;
       bool ok = has;
-      if (has && !c.en.no_ene) { tsc = e_loop(c.en, q, i - 1, j, k, l - 1); ok = tsc > NINF; }
+      if (has && !LC.en.no_ene) { tsc = nl_e_loop(&q, i - 1, j, k, l - 1); ok = tsc > NINF; }
       batch_push(c, w, n, ok, k, l, tsc);
     }
   }
@@ -446,7 +478,7 @@ template <class F> RDEV void walk_outer(const LinCtx& c, int i, int d, WarpLin& 
       int j2 = j + u2;
       double tsc = 0.;
       bool ok = has;
-      if (has && !c.en.no_ene) { tsc = e_loop(c.en, q, i2 - 1, j2, i, j - 1); ok = tsc > NINF; }
+      if (has && !LC.en.no_ene) { tsc = nl_e_loop(&q, i2 - 1, j2, i, j - 1); ok = tsc > NINF; }
       batch_push(c, w, n, ok, i2, j2, tsc);
     }
   }
@@ -477,7 +509,7 @@ template <class F> RDEV void walk_left_flank(const LinCtx& c, int i, int d, Warp
       int j2 = l + u2;
       double tsc = 0.;
       bool ok = has;
-      if (has && !c.en.no_ene) { tsc = e_loop(c.en, q, i - 1, j2, k, l - 1); ok = tsc > NINF; }
+      if (has && !LC.en.no_ene) { tsc = nl_e_loop(&q, i - 1, j2, k, l - 1); ok = tsc > NINF; }
       batch_push(c, w, n, ok, l, j2, tsc);
     }
   }
@@ -508,7 +540,7 @@ template <class F> RDEV void walk_right_flank(const LinCtx& c, int l, int d, War
       int i2 = k - u1;
       double tsc = 0.;
       bool ok = has;
-      if (has && !c.en.no_ene) { tsc = e_loop(c.en, q, i2 - 1, j, k, l - 1); ok = tsc > NINF; }
+      if (has && !LC.en.no_ene) { tsc = nl_e_loop(&q, i2 - 1, j, k, l - 1); ok = tsc > NINF; }
       batch_push(c, w, n, ok, k, i2, tsc);
     }
   }
@@ -519,14 +551,14 @@ template <class F> RDEV void walk_right_flank(const LinCtx& c, int l, int d, War
 
 // ------------------------------------------------------------------------------------------------- inside
 RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
-  const LinHMM& h = c.h;
-  const LinParams& p = c.p;
+  const LinHMM& h = LC.h;
+  const LinParams& p = LC.p;
   const SeqView& q = c.q;
   const int S = q.S, j = i + d, lane = lane_id();
   double* cur = w.curA;
   double* part = w.partA;
   const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
-  const bool ne = c.en.no_ene != 0;
+  const bool ne = LC.en.no_ene != 0;
   const int xl = i < q.L ? q.x[i] : 0, xr = d >= 1 ? q.x[j - 1] : 0;
   const double wsl = i < q.L ? c.wsf[i] : 1., wsr = d >= 1 ? c.wsf[j - 1] : 1.;
   // ---- L(i,j,s) <- L(i,j-1,s1) emitR
@@ -553,9 +585,9 @@ RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin
     bool cPP = cP;
     double f0 = 1., f1 = 1.;
     if (cP && !ne) {
-      double tsc = e_loop(c.en, q, i, j - 1, i + 1, j - 2);
+      double tsc = nl_e_loop(&q, i, j - 1, i + 1, j - 2);
       cPP = tsc > NINF;
-      if (cPP) { f0 = exp(p.lambda0 * tsc); f1 = exp(p.lambda1 * tsc); }
+      if (cPP) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
     }
     const double* srcE = t.aE + cidx(q, i + 1, d - 2);
     const double* srcP = t.aP + cidx(q, j - 1, d - 2);
@@ -597,7 +629,7 @@ RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin
       double v = 0.;
       for (int tt = 0; tt < nk; ++tt) {
         int u = w.kbuf[tt];
-        v += r1[(size_t)u * S + sl] * r2[(size_t)(d - u) * S + sr];
+        v += r1[(unsigned)u * S + sl] * r2[(unsigned)(d - u) * S + sr];
       }
       part[a] = v;
     }
@@ -618,9 +650,9 @@ RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin
     bool c2P = gP;
     double f0 = 1., f1 = 1.;
     if (gP && !ne) {
-      double tsc = e_sum_ext_m(c.en, q, i, j - 1, false) + c.en.mlintern;
+      double tsc = nl_e_ext(&q, i, j - 1, 0) + LC.en.mlintern;
       c2P = tsc > NINF;
-      if (c2P) { f0 = exp(p.lambda0 * tsc); f1 = exp(p.lambda1 * tsc); }
+      if (c2P) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
     }
     w_sync();
     for (int s = lane; s < S; s += WARP_N) {
@@ -666,7 +698,7 @@ RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin
           for (int pp = 0; pp < n; ++pp) {
             int k = w.bi[pp], l = w.bj[pp];
             double a0 = t.aP[cidx(q, l, l - k) + s1];
-            v += a0 * rL[(size_t)(k - i) * S + s2] * rR[(size_t)(j - l) * S + s3] * bf[pp];
+            v += a0 * rL[(unsigned)(k - i) * S + s2] * rR[(unsigned)(j - l) * S + s3] * bf[pp];
           }
           part[a] = v;
         }
@@ -676,13 +708,13 @@ RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin
     double m0 = 1., m1 = 1., h0 = 1., h1 = 1.;
     if (!ne) {
       if (gM) {
-        double tM = e_sum_ext_m(c.en, q, j, i - 1, false) + (c.en.mlclosing + c.en.mlintern);
+        double tM = nl_e_ext(&q, j, i - 1, 0) + (LC.en.mlclosing + LC.en.mlintern);
         cM = tM > NINF;
-        if (cM) { m0 = exp(p.lambda0 * tM); m1 = exp(p.lambda1 * tM); }
+        if (cM) { F2 ff = boltz2(tM); m0 = ff.f0; m1 = ff.f1; }
       }
-      double tH = e_hairpin(c.en, q, i - 1, j);
+      double tH = nl_e_hairpin(&q, i - 1, j);
       cH = tH > NINF;
-      if (cH) { h0 = exp(p.lambda0 * tH); h1 = exp(p.lambda1 * tH); }
+      if (cH) { F2 ff = boltz2(tH); h0 = ff.f0; h1 = ff.f1; }
     }
     for (int s = lane; s < S; s += WARP_N) {
       double x = seg_sum(part, h.q_off, s);
@@ -695,7 +727,7 @@ RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin
   }
   // ---- write back
   {
-    size_t il = cidx(q, i, d), ir = cidx(q, j, d);
+    unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
     for (int s = lane; s < S; s += WARP_N) {
       double vL = cur[PL_L * S + s];
       t.aLl[il + s] = vL;
@@ -711,11 +743,11 @@ RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin
 
 // exterior row, one warp: O(j,s) <- O(i,(s.l,h)) P(i,j,(h,s.r)) ext | O(j-1,s1) emitR
 RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
-  const LinHMM& h = c.h;
-  const LinParams& p = c.p;
+  const LinHMM& h = LC.h;
+  const LinParams& p = LC.p;
   const SeqView& q = c.q;
   const int S = q.S, L = q.L, lane = lane_id();
-  const bool ne = c.en.no_ene != 0;
+  const bool ne = LC.en.no_ene != 0;
   double* part = w.partA;
   double* cur = w.curA;
   for (int s = lane; s < S; s += WARP_N) t.aO[s] = (s == h.s00) ? 1. : 0.;
@@ -730,7 +762,7 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
         double v = part[a];
         for (int pp = 0; pp < n; ++pp) {
           int i = w.bi[pp];
-          v += t.aO[(size_t)i * S + sl] * t.aP[cidx(q, j, j - i) + sr] * bf[pp];
+          v += t.aO[(unsigned)i * S + sl] * t.aP[cidx(q, j, j - i) + sr] * bf[pp];
         }
         part[a] = v;
       }
@@ -743,7 +775,7 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
         int u = u0 + lane;
         bool ok = u <= dmax && row_bit(rj, u);
         double tsc = 0.;
-        if (ok && !ne) { tsc = e_sum_ext_m(c.en, q, j - u, j - 1, true); ok = tsc > NINF; }
+        if (ok && !ne) { tsc = nl_e_ext(&q, j - u, j - 1, 1); ok = tsc > NINF; }
         batch_push(c, w, n, ok, j - u, j, tsc);
       }
       w_sync();
@@ -755,12 +787,12 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
     const int xr = q.x[j - 1];
     const double wsr = c.wsf[j - 1];
     for (int a = lane; a < h.n_right; a += WARP_N) {
-      double v = t.aO[(size_t)(j - 1) * S + ld_ro(h.r_src + a)] * ld_ro(p.r_w + a * 5 + xr);
+      double v = t.aO[(unsigned)(j - 1) * S + ld_ro(h.r_src + a)] * ld_ro(p.r_w + a * 5 + xr);
       if (ld_ro(h.r_flag + a) & 1) v *= wsr;
       part[a] = v;
     }
     w_sync();
-    for (int s = lane; s < S; s += WARP_N) t.aO[(size_t)j * S + s] = cur[s] + seg_sum(part, h.r_off, s);
+    for (int s = lane; s < S; s += WARP_N) t.aO[(unsigned)j * S + s] = cur[s] + seg_sum(part, h.r_off, s);
     w_sync();
   }
 }
@@ -777,11 +809,11 @@ template <int NCH> struct EhAcc {
 
 // exterior row top-down, one warp.  bO(L,.) must hold the root weights.
 template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
-  const LinHMM& h = c.h;
-  const LinParams& p = c.p;
+  const LinHMM& h = LC.h;
+  const LinParams& p = LC.p;
   const SeqView& q = c.q;
   const int S = q.S, L = q.L, lane = lane_id(), NM = w.n_max;
-  const bool ne = c.en.no_ene != 0;
+  const bool ne = LC.en.no_ene != 0;
   for (int i = L - 1; i >= 0; --i) {
     for (int a = lane; a < h.n_split; a += WARP_N)
       for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
@@ -796,7 +828,7 @@ template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, Wa
         for (int pp = 0; pp < n; ++pp) {
           int j = w.bi[pp];
           double term = t.aP[cidx(q, j, j - i) + sr] * bf[pp];
-          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bO[ch * t.boch + (size_t)j * S + s] * term;
+          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bO[ch * t.boch + (unsigned)j * S + s] * term;
         }
         for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
       }
@@ -809,7 +841,7 @@ template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, Wa
         int u = u0 + lane;
         bool ok = u <= dmax && row_bit(ri, u);
         double tsc = 0.;
-        if (ok && !ne) { tsc = e_sum_ext_m(c.en, q, i, i + u - 1, true); ok = tsc > NINF; }
+        if (ok && !ne) { tsc = nl_e_ext(&q, i, i + u - 1, 1); ok = tsc > NINF; }
         batch_push(c, w, n, ok, i + u, i, tsc);
       }
       w_sync();
@@ -827,9 +859,9 @@ template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, Wa
       int sp = ld_ro(h.r_tgt + a), ch_s = ld_ro(h.r_src + a);
       double wt = ld_ro(p.r_w + a * 5 + xr);
       if (ld_ro(h.r_flag + a) & 1) wt *= wsr;
-      double ac = t.aO[(size_t)i * S + ch_s];
+      double ac = t.aO[(unsigned)i * S + ch_s];
       for (int ch = 0; ch < NCH; ++ch) {
-        double contrib = t.bO[ch * t.boch + (size_t)(i + 1) * S + sp] * wt;
+        double contrib = t.bO[ch * t.boch + (unsigned)(i + 1) * S + sp] * wt;
         w.partA[ch * NM + pz] = contrib;
         if (!p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
       }
@@ -837,22 +869,22 @@ template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, Wa
     w_sync();
     for (int s = lane; s < S; s += WARP_N)
       for (int ch = 0; ch < NCH; ++ch)
-        t.bO[ch * t.boch + (size_t)i * S + s] = w.curB[ch * S + s] + seg_sum(w.partA + ch * NM, h.rT_off, s);
+        t.bO[ch * t.boch + (unsigned)i * S + s] = w.curB[ch * S + s] + seg_sum(w.partA + ch * NM, h.rT_off, s);
     w_sync();
   }
 }
 
 template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w, EhAcc<NCH>& eh) {
-  const LinHMM& h = c.h;
-  const LinParams& p = c.p;
+  const LinHMM& h = LC.h;
+  const LinParams& p = LC.p;
   const SeqView& q = c.q;
   const int S = q.S, j = i + d, lane = lane_id(), L = q.L, W = q.W, NM = w.n_max;
-  const bool ne = c.en.no_ene != 0;
+  const bool ne = LC.en.no_ene != 0;
   const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
   double* cA = w.curA;
   double* cB = w.curB;
 #define CB(ch, pl, s) cB[((ch) * NPLANE + (pl)) * S + (s)]
-  const size_t il = cidx(q, i, d), ir = cidx(q, j, d);
+  const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
   // inside values of this cell (for the posteriors that are counted)
   for (int s = lane; s < S; s += WARP_N) {
     cA[PL_L * S + s] = t.aLl[il + s];
@@ -870,7 +902,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
   if (gE) {
     const int xl = q.x[i - 1], xr = q.x[j];
     const double wsl = c.wsf[i - 1], wsr = c.wsf[j];
-    const size_t pb = cidx(q, i - 1, d + 2);
+    const unsigned pb = cidx(q, i - 1, d + 2);
     for (int pz = lane; pz < h.n_pair; pz += WARP_N) {
       int a = ld_ro(h.pT_ord + pz);
       int s = ld_ro(h.p_tgt + a), s1 = ld_ro(h.p_src + a), fl = ld_ro(h.p_flag + a);
@@ -895,15 +927,15 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
     bool cM = gE;
     double tM = 0., m0 = 1., m1 = 1.;
     if (gE && !ne) {
-      tM = e_sum_ext_m(c.en, q, j, i - 1, false) + (c.en.mlclosing + c.en.mlintern);
+      tM = nl_e_ext(&q, j, i - 1, 0) + (LC.en.mlclosing + LC.en.mlintern);
       cM = tM > NINF;
-      if (cM) { m0 = exp(p.lambda0 * tM); m1 = exp(p.lambda1 * tM); }
+      if (cM) { F2 ff = boltz2(tM); m0 = ff.f0; m1 = ff.f1; }
     }
     const bool okM = ok_M(q, i - 1, d + 1);
     if (okM) {
       const int xl = q.x[i - 1];
       const double wsl = c.wsf[i - 1];
-      const size_t pb = cidx(q, i - 1, d + 1);
+      const unsigned pb = cidx(q, i - 1, d + 1);
       for (int pz = lane; pz < h.n_left; pz += WARP_N) {
         int a = ld_ro(h.lT_ord + pz);
         int sp = ld_ro(h.l_tgt + a), s1 = ld_ro(h.l_src + a);
@@ -947,7 +979,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
         nk += w_popc(bal);
       }
       w_sync();
-      const size_t rb = cidx(q, i, 0);
+      const unsigned rb = cidx(q, i, 0);
       for (int pz = lane; pz < h.n_split; pz += WARP_N) {
         int a = ld_ro(h.spL_ord + pz);
         int s = ld_ro(h.sp_tgt + a), sr = ld_ro(h.sp_r + a);
@@ -956,7 +988,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
         for (int tt = 0; tt < nk; ++tt) {
           int d2 = w.kbuf[tt];
           double sib = t.a2[cidx(q, i + d2, d2 - d) + sr];
-          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBl[ch * t.bch + rb + (size_t)d2 * S + s] * sib;
+          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBl[ch * t.bch + rb + (unsigned)d2 * S + s] * sib;
         }
         for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
       }
@@ -982,7 +1014,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
         nk += w_popc(bal);
       }
       w_sync();
-      const size_t rb = cidx(q, j, 0);
+      const unsigned rb = cidx(q, j, 0);
       for (int pz = lane; pz < h.n_split; pz += WARP_N) {
         int a = ld_ro(h.spR_ord + pz);
         int s = ld_ro(h.sp_tgt + a), sl = ld_ro(h.sp_l + a);
@@ -991,7 +1023,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
         for (int tt = 0; tt < nk; ++tt) {
           int d2 = w.kbuf[tt];
           double sib = t.a1[cidx(q, j - d2, d2 - d) + sl];
-          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBr[ch * t.bch + rb + (size_t)d2 * S + s] * sib;
+          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBr[ch * t.bch + rb + (unsigned)d2 * S + s] * sib;
         }
         for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
       }
@@ -1002,7 +1034,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
       if (ok_B(q, i, d + 1)) {
         const int xr = q.x[j];
         const double wsr = c.wsf[j];
-        const size_t pb = cidx(q, i, d + 1);
+        const unsigned pb = cidx(q, i, d + 1);
         for (int pz = lane; pz < h.n_right; pz += WARP_N) {
           int a = ld_ro(h.rT_ord + pz);
           int sp = ld_ro(h.r_tgt + a), s1 = ld_ro(h.r_src + a);
@@ -1029,9 +1061,9 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
       bool c2P = true;
       double tsc = 0., f0 = 1., f1 = 1.;
       if (!ne) {
-        tsc = e_sum_ext_m(c.en, q, i, j - 1, false) + c.en.mlintern;
+        tsc = nl_e_ext(&q, i, j - 1, 0) + LC.en.mlintern;
         c2P = tsc > NINF;
-        if (c2P) { f0 = exp(p.lambda0 * tsc); f1 = exp(p.lambda1 * tsc); }
+        if (c2P) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
       }
       if (c2P)
         for (int s = lane; s < S; s += WARP_N) {
@@ -1049,14 +1081,14 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
       bool cPP = true;
       double tsc = 0., f0 = 1., f1 = 1.;
       if (!ne) {
-        tsc = e_loop(c.en, q, i - 1, j, i, j - 1);
+        tsc = nl_e_loop(&q, i - 1, j, i, j - 1);
         cPP = tsc > NINF;
-        if (cPP) { f0 = exp(p.lambda0 * tsc); f1 = exp(p.lambda1 * tsc); }
+        if (cPP) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
       }
       if (cPP) {
         const int xl = q.x[i - 1], xr = q.x[j];
         const double wsl = c.wsf[i - 1], wsr = c.wsf[j];
-        const size_t pb = cidx(q, i - 1, d + 2);
+        const unsigned pb = cidx(q, i - 1, d + 2);
         for (int pz = lane; pz < h.n_pair; pz += WARP_N) {
           int a = ld_ro(h.pT_ord + pz);
           int s = ld_ro(h.p_tgt + a), s1 = ld_ro(h.p_src + a), fl = ld_ro(h.p_flag + a);
@@ -1084,19 +1116,19 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
       bool cX = true;
       double tsc = 0., f0 = 1., f1 = 1.;
       if (!ne) {
-        tsc = e_sum_ext_m(c.en, q, i, j - 1, true);
+        tsc = nl_e_ext(&q, i, j - 1, 1);
         cX = tsc > NINF;
-        if (cX) { f0 = exp(p.lambda0 * tsc); f1 = exp(p.lambda1 * tsc); }
+        if (cX) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
       }
       if (cX) {
         for (int pz = lane; pz < h.n_split; pz += WARP_N) {
           int a = ld_ro(h.spR_ord + pz);
           int s = ld_ro(h.sp_tgt + a), sl_ = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
           int sl = ld_ro(h.slot + s);
-          double term = t.aO[(size_t)i * S + sl_] * (sl ? f1 : f0);
+          double term = t.aO[(unsigned)i * S + sl_] * (sl ? f1 : f0);
           double ac = cA[PL_P * S + sr];
           for (int ch = 0; ch < NCH; ++ch) {
-            double contrib = t.bO[ch * t.boch + (size_t)j * S + s] * term;
+            double contrib = t.bO[ch * t.boch + (unsigned)j * S + s] * term;
             w.partA[ch * NM + pz] = contrib;
             eh.add(ch, sl, tsc * contrib * ac);
           }
@@ -1123,7 +1155,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
             int i2 = w.bi[pp], j2 = w.bj[pp];
             double term = t.aLl[cidx(q, i2, i - i2) + s2] * t.aLr[cidx(q, j2, j2 - j) + s3] * bf[pp];
             double tsc = w.bt[pp];
-            size_t eb = cidx(q, i2, j2 - i2) + s;
+            unsigned eb = cidx(q, i2, j2 - i2) + s;
             for (int ch = 0; ch < NCH; ++ch) {
               double x = t.bEl[ch * t.bch + eb] * term;
               v[ch] += x;
@@ -1151,9 +1183,9 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
       bool cH = true;
       double tH = 0., h0 = 1., h1 = 1.;
       if (!ne) {
-        tH = e_hairpin(c.en, q, i - 1, j);
+        tH = nl_e_hairpin(&q, i - 1, j);
         cH = tH > NINF;
-        if (cH) { h0 = exp(p.lambda0 * tH); h1 = exp(p.lambda1 * tH); }
+        if (cH) { F2 ff = boltz2(tH); h0 = ff.f0; h1 = ff.f1; }
       }
       if (cH)
         for (int s = lane; s < S; s += WARP_N) {
@@ -1171,7 +1203,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
     if (d + 1 <= W && j + 1 <= L) {
       const int xr = q.x[j];
       const double wsr = c.wsf[j];
-      const size_t pb = cidx(q, i, d + 1);
+      const unsigned pb = cidx(q, i, d + 1);
       for (int pz = lane; pz < h.n_right; pz += WARP_N) {
         int a = ld_ro(h.rT_ord + pz);
         int fl = ld_ro(h.r_flag + a);
@@ -1200,7 +1232,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
         for (int a = lane; a < h.n_quad; a += WARP_N)
           for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
         w_sync();
-        const size_t eb = cidx(q, i, 0);
+        const unsigned eb = cidx(q, i, 0);
         walk_left_flank(c, i, d, w, [&](int n) {
           for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
             int a = ld_ro(h.qL_ord + pz);
@@ -1211,7 +1243,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
             for (int pp = 0; pp < n; ++pp) {
               int l = w.bi[pp], j2 = w.bj[pp];
               double term = t.aP[cidx(q, l, l - j) + s1] * t.aLr[cidx(q, j2, j2 - l) + s3] * bf[pp];
-              for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEl[ch * t.bch + eb + (size_t)(j2 - i) * S + s] * term;
+              for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEl[ch * t.bch + eb + (unsigned)(j2 - i) * S + s] * term;
             }
             for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
           }
@@ -1224,7 +1256,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
         for (int a = lane; a < h.n_quad; a += WARP_N)
           for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
         w_sync();
-        const size_t eb = cidx(q, j, 0);
+        const unsigned eb = cidx(q, j, 0);
         walk_right_flank(c, i, d, w, [&](int n) {
           for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
             int a = ld_ro(h.qR_ord + pz);
@@ -1235,7 +1267,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
             for (int pp = 0; pp < n; ++pp) {
               int k = w.bi[pp], i2 = w.bj[pp];
               double term = t.aP[cidx(q, i, i - k) + s1] * t.aLl[cidx(q, i2, k - i2) + s2] * bf[pp];
-              for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEr[ch * t.bch + eb + (size_t)(j - i2) * S + s] * term;
+              for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEr[ch * t.bch + eb + (unsigned)(j - i2) * S + s] * term;
             }
             for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
           }
@@ -1249,7 +1281,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
   // ---- write back
   for (int s = lane; s < S; s += WARP_N)
     for (int ch = 0; ch < NCH; ++ch) {
-      const size_t o = ch * t.bch;
+      const unsigned o = ch * t.bch;
       if (d >= 1) t.bL[o + il + s] = CB(ch, PL_L, s);
       if (gP) t.bP[o + il + s] = CB(ch, PL_P, s);
       if (gE) { t.bEl[o + il + s] = CB(ch, PL_E, s); t.bEr[o + ir + s] = CB(ch, PL_E, s); }

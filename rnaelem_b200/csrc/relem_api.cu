@@ -681,10 +681,11 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
   if (eo.prof) {
     unsigned long long pr[16];
     if (Dev::d2h(pr, eo.prof, sizeof(pr))) {
-      static const char* pn[5] = {"phase:prepare+bpp_filter", "phase:emit+inside", "phase:zero_Q", "phase:outside", "phase:fold+store"};
+      static const char* pn[9] = {"phase:prepare+bpp_filter", "phase:emit+inside", "phase:zero_Q", "phase:outside", "phase:fold+store",
+                                  "phase:k0_inside", "phase:k0_ext", "phase:k0_outside", "phase:ext_rows"};
       double tot = 0;
-      for (int k = 0; k < 5; ++k) tot += (double)pr[k];
-      for (int k = 0; k < 5; ++k) c->timing.push_back(TimingEntry{pn[k], tot > 0 ? (float)(pr[k] / tot) : 0.f, 0});
+      for (int k = 0; k < 9; ++k) tot += (double)pr[k];
+      for (int k = 0; k < 9; ++k) c->timing.push_back(TimingEntry{pn[k], tot > 0 ? (float)(pr[k] / tot) : 0.f, 0});
     }
   }
   out->fn = res[0]; out->sum_eff = res[1]; out->n_skipped = (int64_t)res[2];
