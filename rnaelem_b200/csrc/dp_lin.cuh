@@ -375,23 +375,25 @@ struct WarpLin {
   double* pcnt;   // [NCH][n_pair*25] CTA-shared (atomics)
   int n_max;
 };
-RHD int warp_lin_bytes(int S, int Wmax, int nch, int n_max, int n_right, int n_left) {
-  int n = (NPLANE * S + nch * NPLANE * S + 2 * nch * n_max + 3 * LIN_CAP + nch * 5 * (n_right + n_left)) * 8 +
-          (2 * LIN_CAP + Wmax + 4) * 4;
+// inside = true: only what the inside pass needs (no outside staging, no counts)
+RHD int warp_lin_bytes(int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside) {
+  int n = inside ? (NPLANE * S + n_max + 3 * LIN_CAP) * 8
+                 : (NPLANE * S + nch * NPLANE * S + 2 * nch * n_max + 3 * LIN_CAP + nch * 5 * (n_right + n_left)) * 8;
+  n += (2 * LIN_CAP + Wmax + 4) * 4;
   return (n + 15) & ~15;
 }
-RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n_max, int n_right, int n_left) {
+RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside) {
   WarpLin w;
   double* p = (double*)base;
   w.curA = p; p += NPLANE * S;
-  w.curB = p; p += nch * NPLANE * S;
-  w.partA = p; p += nch * n_max;
-  w.partT = p; p += nch * n_max;
+  w.curB = p; p += inside ? 0 : nch * NPLANE * S;
+  w.partA = p; p += inside ? n_max : nch * n_max;
+  w.partT = p; p += inside ? 0 : nch * n_max;
   w.bt = p; p += LIN_CAP;
   w.bf0 = p; p += LIN_CAP;
   w.bf1 = p; p += LIN_CAP;
-  w.cntR = p; p += nch * 5 * n_right;
-  w.cntL = p; p += nch * 5 * n_left;
+  w.cntR = p; p += inside ? 0 : nch * 5 * n_right;
+  w.cntL = p; p += inside ? 0 : nch * 5 * n_left;
   int* ip = (int*)p;
   w.bi = ip; ip += LIN_CAP;
   w.bj = ip; ip += LIN_CAP;
@@ -550,65 +552,98 @@ template <class F> RDEV void walk_right_flank(const LinCtx& c, int l, int d, War
 }
 
 // ------------------------------------------------------------------------------------------------- inside
-RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
+// The cell update is split into four PHASES that a warp runs one after the other over all of its cells of a
+// diagonal (phase-major order): the instruction working set at any time is one phase (a few hundred instructions)
+// instead of the whole cell update, which matters because the SM's instruction cache holds only ~2K instructions.
+// Values that flow between phases of the same cell (P -> 2, B -> M, {M,L} -> E) go through the tables themselves
+// (same warp, L1/L2 hits).
+//
+// ---- phase L: L(i,j,s) <- L(i,j-1,s1) emitR   (every cell)
+RDEV void lin_in_L(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
   const SeqView& q = c.q;
   const int S = q.S, j = i + d, lane = lane_id();
-  double* cur = w.curA;
-  double* part = w.partA;
-  const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
-  const bool ne = LC.en.no_ene != 0;
-  const int xl = i < q.L ? q.x[i] : 0, xr = d >= 1 ? q.x[j - 1] : 0;
-  const double wsl = i < q.L ? c.wsf[i] : 1., wsr = d >= 1 ? c.wsf[j - 1] : 1.;
-  // ---- L(i,j,s) <- L(i,j-1,s1) emitR
+  const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
   if (d == 0) {
-    for (int s = lane; s < S; s += WARP_N) cur[PL_L * S + s] = ld_ro(h.slot + s) ? 0. : 1.;
-  } else {
-    const double* src = t.aLl + cidx(q, i, d - 1);
-    for (int a = lane; a < h.n_right; a += WARP_N) {
-      int fl = ld_ro(h.r_flag + a);
-      double v = 0.;
-      if (fl & 2) {
-        v = src[ld_ro(h.r_src + a)] * ld_ro(p.r_w + a * 5 + xr);
-        if (fl & 1) v *= wsr;
-      }
-      part[a] = v;
+    for (int s = lane; s < S; s += WARP_N) {
+      double v = ld_ro(h.slot + s) ? 0. : 1.;
+      t.aLl[il + s] = v;
+      t.aLr[ir + s] = v;
     }
-    w_sync();
-    for (int s = lane; s < S; s += WARP_N) cur[PL_L * S + s] = seg_sum(part, h.r_off, s);
+    return;
+  }
+  double* part = w.partA;
+  const int xr = q.x[j - 1];
+  const double wsr = c.wsf[j - 1];
+  const double* src = t.aLl + cidx(q, i, d - 1);
+  for (int a = lane; a < h.n_right; a += WARP_N) {
+    int fl = ld_ro(h.r_flag + a);
+    double v = 0.;
+    if (fl & 2) {
+      v = src[ld_ro(h.r_src + a)] * ld_ro(p.r_w + a * 5 + xr);
+      if (fl & 1) v *= wsr;
+    }
+    part[a] = v;
   }
   w_sync();
-  // ---- P(i,j,s) <- E(i+1,j-1,s1) | P(i+1,j-1,s1)
-  if (gP) {
-    const bool cE = ok_E(q, i + 1, d - 2), cP = ok_P(q, i + 1, d - 2);
-    bool cPP = cP;
-    double f0 = 1., f1 = 1.;
-    if (cP && !ne) {
-      double tsc = nl_e_loop(&q, i, j - 1, i + 1, j - 2);
-      cPP = tsc > NINF;
-      if (cPP) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
-    }
-    const double* srcE = t.aE + cidx(q, i + 1, d - 2);
-    const double* srcP = t.aP + cidx(q, j - 1, d - 2);
-    for (int a = lane; a < h.n_pair; a += WARP_N) {
-      double v = 0.;
-      if (cE || cPP) {
-        int fl = ld_ro(h.p_flag + a), s1 = ld_ro(h.p_src + a);
-        double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr);
-        if (fl & 1) wt *= wsl;
-        if (fl & 2) wt *= wsr;
-        if (cE) v += srcE[s1] * wt;
-        if (cPP) v += srcP[s1] * wt * (ld_ro(h.slot + ld_ro(h.p_tgt + a)) ? f1 : f0);
-      }
-      part[a] = v;
-    }
-    w_sync();
-    for (int s = lane; s < S; s += WARP_N) cur[PL_P * S + s] = seg_sum(part, h.p_off, s);
-    w_sync();
+  for (int s = lane; s < S; s += WARP_N) {
+    double v = seg_sum(part, h.r_off, s);
+    t.aLl[il + s] = v;
+    t.aLr[ir + s] = v;
   }
+  w_sync();
+}
+
+// ---- phase P: P(i,j,s) <- E(i+1,j-1,s1) | P(i+1,j-1,s1)   (cells with an allowed pair)
+RDEV void lin_in_P(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
+  const LinHMM& h = LC.h;
+  const LinParams& p = LC.p;
+  const SeqView& q = c.q;
+  const int S = q.S, j = i + d, lane = lane_id();
+  double* part = w.partA;
+  const bool ne = LC.en.no_ene != 0;
+  const int xl = q.x[i], xr = q.x[j - 1];
+  const double wsl = c.wsf[i], wsr = c.wsf[j - 1];
+  const bool cE = ok_E(q, i + 1, d - 2), cP = ok_P(q, i + 1, d - 2);
+  bool cPP = cP;
+  double f0 = 1., f1 = 1.;
+  if (cP && !ne) {
+    double tsc = nl_e_loop(&q, i, j - 1, i + 1, j - 2);
+    cPP = tsc > NINF;
+    if (cPP) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
+  }
+  const double* srcE = t.aE + cidx(q, i + 1, d - 2);
+  const double* srcP = t.aP + cidx(q, j - 1, d - 2);
+  for (int a = lane; a < h.n_pair; a += WARP_N) {
+    double v = 0.;
+    if (cE || cPP) {
+      int fl = ld_ro(h.p_flag + a), s1 = ld_ro(h.p_src + a);
+      double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr);
+      if (fl & 1) wt *= wsl;
+      if (fl & 2) wt *= wsr;
+      if (cE) v += srcE[s1] * wt;
+      if (cPP) v += srcP[s1] * wt * (ld_ro(h.slot + ld_ro(h.p_tgt + a)) ? f1 : f0);
+    }
+    part[a] = v;
+  }
+  w_sync();
+  const unsigned ir = cidx(q, j, d);
+  for (int s = lane; s < S; s += WARP_N) t.aP[ir + s] = seg_sum(part, h.p_off, s);
+  w_sync();
+}
+
+// ---- phase B: B <- 1 2;  2 <- 2 emitR | P;  1 <- 2 | B;  M <- M emitL | B   (cells with gB or gM)
+RDEV void lin_in_B(const LinCtx& c, const CTabs& t, int i, int d, bool gP, bool gB, bool gM, WarpLin& w) {
+  const LinHMM& h = LC.h;
+  const LinParams& p = LC.p;
+  const SeqView& q = c.q;
+  const int S = q.S, j = i + d, lane = lane_id();
+  double* cur = w.curA;   // [0..S) B of this cell
+  double* part = w.partA;
+  const bool ne = LC.en.no_ene != 0;
+  const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
   if (gB) {
-    // ---- B(i,j,s) <- 1(i,k,(s.l,h)) 2(k,j,(h,s.r))
     int nk = 0;
     {
       const unsigned* ri = q.lf + i * q.mw;
@@ -623,22 +658,27 @@ RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin
       w_sync();
     }
     const double* r1 = t.a1 + cidx(q, i, 0);
-    const double* r2 = t.a2 + cidx(q, j, 0);
+    const double* r2 = t.a2 + cidx(q, j, 0) + (unsigned)d * S;
     for (int a = lane; a < h.n_split; a += WARP_N) {
-      int sl = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
-      double v = 0.;
-      for (int tt = 0; tt < nk; ++tt) {
-        int u = w.kbuf[tt];
-        v += r1[(unsigned)u * S + sl] * r2[(unsigned)(d - u) * S + sr];
+      const double* p1 = r1 + ld_ro(h.sp_l + a);
+      const double* p2 = r2 + ld_ro(h.sp_r + a);
+      double v0 = 0., v1 = 0.;
+      int tt = 0;
+      for (; tt + 1 < nk; tt += 2) {
+        int u0 = w.kbuf[tt] * S, u1 = w.kbuf[tt + 1] * S;
+        v0 += p1[u0] * p2[-u0];
+        v1 += p1[u1] * p2[-u1];
       }
-      part[a] = v;
+      if (tt < nk) { int u0 = w.kbuf[tt] * S; v0 += p1[u0] * p2[-u0]; }
+      part[a] = v0 + v1;
     }
     w_sync();
-    for (int s = lane; s < S; s += WARP_N) cur[PL_B * S + s] = seg_sum(part, h.sp_off, s);
+    for (int s = lane; s < S; s += WARP_N) cur[s] = seg_sum(part, h.sp_off, s);
     w_sync();
-    // ---- 2(i,j,s) <- 2(i,j-1,s1) emitR | P(i,j,s);  1 <- 2 | B
+    const int xr = q.x[j - 1];
+    const double wsr = c.wsf[j - 1];
     const bool ok2 = ok_B(q, i, d - 1);
-    const double* src2 = t.a2 + cidx(q, j - 1, d >= 1 ? d - 1 : 0);
+    const double* src2 = t.a2 + cidx(q, j - 1, d - 1);
     for (int a = lane; a < h.n_right; a += WARP_N) {
       double v = 0.;
       if (ok2) {
@@ -657,14 +697,15 @@ RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin
     w_sync();
     for (int s = lane; s < S; s += WARP_N) {
       double x = seg_sum(part, h.r_off, s);
-      if (c2P) x += cur[PL_P * S + s] * (ld_ro(h.slot + s) ? f1 : f0);
-      cur[PL_2 * S + s] = x;
-      cur[PL_1 * S + s] = x + cur[PL_B * S + s];
+      if (c2P) x += t.aP[ir + s] * (ld_ro(h.slot + s) ? f1 : f0);
+      t.a2[ir + s] = x;
+      t.a1[il + s] = x + cur[s];
     }
     w_sync();
   }
-  // ---- M(i,j,s) <- M(i+1,j,s1) emitL | B(i,j,s)
   if (gM) {
+    const int xl = q.x[i];
+    const double wsl = c.wsf[i];
     const bool okM = ok_M(q, i + 1, d - 1);
     const double* srcM = t.aM + cidx(q, i + 1, d - 1);
     for (int a = lane; a < h.n_left; a += WARP_N) {
@@ -678,67 +719,78 @@ RDEV void lin_inside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin
     w_sync();
     for (int s = lane; s < S; s += WARP_N) {
       double x = seg_sum(part, h.l_off, s);
-      if (gB) x += cur[PL_B * S + s];
-      cur[PL_M * S + s] = x;
+      if (gB) x += cur[s];
+      t.aM[il + s] = x;
     }
     w_sync();
   }
-  // ---- E(i,j,s) <- M(i,j,s) | L(i,j,s) hairpin | P(k,l,s1) L(i,k,s2) L(l,j,s3)
-  if (gE) {
-    for (int a = lane; a < h.n_quad; a += WARP_N) part[a] = 0.;
-    w_sync();
-    if (h.n_quad > 0) {
-      const double* rL = t.aLl + cidx(q, i, 0);
-      const double* rR = t.aLr + cidx(q, j, 0);
-      walk_inner(c, i, d, w, [&](int n) {
-        for (int a = lane; a < h.n_quad; a += WARP_N) {
-          int s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a), s3 = ld_ro(h.q_s3 + a);
-          const double* bf = ld_ro(h.slot + ld_ro(h.q_tgt + a)) ? w.bf1 : w.bf0;
-          double v = part[a];
-          for (int pp = 0; pp < n; ++pp) {
-            int k = w.bi[pp], l = w.bj[pp];
-            double a0 = t.aP[cidx(q, l, l - k) + s1];
-            v += a0 * rL[(unsigned)(k - i) * S + s2] * rR[(unsigned)(j - l) * S + s3] * bf[pp];
-          }
-          part[a] = v;
+}
+
+// ---- phase E: E(i,j,s) <- M(i,j,s) | L(i,j,s) hairpin | P(k,l,s1) L(i,k,s2) L(l,j,s3)   (cells enclosed by a pair)
+RDEV void lin_in_E(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpLin& w) {
+  const LinHMM& h = LC.h;
+  const SeqView& q = c.q;
+  const int S = q.S, j = i + d, lane = lane_id();
+  double* part = w.partA;
+  const bool ne = LC.en.no_ene != 0;
+  const unsigned il = cidx(q, i, d);
+  for (int a = lane; a < h.n_quad; a += WARP_N) part[a] = 0.;
+  w_sync();
+  if (h.n_quad > 0) {
+    const double* rL = t.aLl + cidx(q, i, 0);
+    const double* rR = t.aLr + cidx(q, j, 0);
+    walk_inner(c, i, d, w, [&](int n) {
+      for (int a = lane; a < h.n_quad; a += WARP_N) {
+        int s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a), s3 = ld_ro(h.q_s3 + a);
+        const double* bf = ld_ro(h.slot + ld_ro(h.q_tgt + a)) ? w.bf1 : w.bf0;
+        double v = part[a];
+        for (int pp = 0; pp < n; ++pp) {
+          int k = w.bi[pp], l = w.bj[pp];
+          double a0 = t.aP[cidx(q, l, l - k) + s1];
+          v += a0 * rL[(unsigned)(k - i) * S + s2] * rR[(unsigned)(j - l) * S + s3] * bf[pp];
         }
-      });
-    }
-    bool cM = gM, cH = true;
-    double m0 = 1., m1 = 1., h0 = 1., h1 = 1.;
-    if (!ne) {
-      if (gM) {
-        double tM = nl_e_ext(&q, j, i - 1, 0) + (LC.en.mlclosing + LC.en.mlintern);
-        cM = tM > NINF;
-        if (cM) { F2 ff = boltz2(tM); m0 = ff.f0; m1 = ff.f1; }
+        part[a] = v;
       }
-      double tH = nl_e_hairpin(&q, i - 1, j);
-      cH = tH > NINF;
-      if (cH) { F2 ff = boltz2(tH); h0 = ff.f0; h1 = ff.f1; }
-    }
-    for (int s = lane; s < S; s += WARP_N) {
-      double x = seg_sum(part, h.q_off, s);
-      int sl = ld_ro(h.slot + s);
-      if (cM) x += cur[PL_M * S + s] * (sl ? m1 : m0);
-      if (cH && ld_ro(h.is_loop + s)) x += cur[PL_L * S + s] * (sl ? h1 : h0);
-      cur[PL_E * S + s] = x;
-    }
-    w_sync();
+    });
   }
-  // ---- write back
-  {
-    unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
-    for (int s = lane; s < S; s += WARP_N) {
-      double vL = cur[PL_L * S + s];
-      t.aLl[il + s] = vL;
-      t.aLr[ir + s] = vL;
-      if (gP) t.aP[ir + s] = cur[PL_P * S + s];
-      if (gB) { t.a1[il + s] = cur[PL_1 * S + s]; t.a2[ir + s] = cur[PL_2 * S + s]; }
-      if (gM) t.aM[il + s] = cur[PL_M * S + s];
-      if (gE) t.aE[il + s] = cur[PL_E * S + s];
+  bool cM = gM, cH = true;
+  double m0 = 1., m1 = 1., h0 = 1., h1 = 1.;
+  if (!ne) {
+    if (gM) {
+      double tM = nl_e_ext(&q, j, i - 1, 0) + (LC.en.mlclosing + LC.en.mlintern);
+      cM = tM > NINF;
+      if (cM) { F2 ff = boltz2(tM); m0 = ff.f0; m1 = ff.f1; }
     }
+    double tH = nl_e_hairpin(&q, i - 1, j);
+    cH = tH > NINF;
+    if (cH) { F2 ff = boltz2(tH); h0 = ff.f0; h1 = ff.f1; }
+  }
+  for (int s = lane; s < S; s += WARP_N) {
+    double x = seg_sum(part, h.q_off, s);
+    int sl = ld_ro(h.slot + s);
+    if (cM) x += t.aM[il + s] * (sl ? m1 : m0);
+    if (cH && ld_ro(h.is_loop + s)) x += t.aLl[il + s] * (sl ? h1 : h0);
+    t.aE[il + s] = x;
   }
   w_sync();
+}
+
+// one diagonal of the inside pass: the warp's cells (static interleaved assignment), phase by phase
+RDEV void lin_inside_diag(const LinCtx& c, const CTabs& t, int d, WarpLin& w) {
+  const SeqView& q = c.q;
+  const int ncell = q.L + 1 - d, w0 = warp_id(), nw = n_warps();
+  for (int i = w0; i < ncell; i += nw) lin_in_L(c, t, i, d, w);
+  if (d >= q.min_pair) {
+    for (int i = w0; i < ncell; i += nw)
+      if (ok_P(q, i, d)) lin_in_P(c, t, i, d, w);
+    for (int i = w0; i < ncell; i += nw) {
+      bool gB = ok_B(q, i, d), gM = ok_M(q, i, d);
+      if (gB || gM) lin_in_B(c, t, i, d, ok_P(q, i, d), gB, gM, w);
+    }
+  }
+  if (d >= 3)
+    for (int i = w0; i < ncell; i += nw)
+      if (ok_E(q, i, d)) lin_in_E(c, t, i, d, ok_M(q, i, d), w);
 }
 
 // exterior row, one warp: O(j,s) <- O(i,(s.l,h)) P(i,j,(h,s.r)) ext | O(j-1,s1) emitR
@@ -874,31 +926,17 @@ template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, Wa
   }
 }
 
-template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w, EhAcc<NCH>& eh) {
+// ---- outside, phase EM: E(i,j,s1) <- parent P(i-1,j+1,s) (pair emission at i-1 and j);
+//                         M(i,j,s)  <- E(i,j,s) | parent M(i-1,j,sp) emitting x[i-1]
+template <int NCH>
+RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, bool gM, WarpLin& w, EhAcc<NCH>& eh) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
   const SeqView& q = c.q;
-  const int S = q.S, j = i + d, lane = lane_id(), L = q.L, W = q.W, NM = w.n_max;
+  const int S = q.S, j = i + d, lane = lane_id(), NM = w.n_max;
   const bool ne = LC.en.no_ene != 0;
-  const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
-  double* cA = w.curA;
-  double* cB = w.curB;
-#define CB(ch, pl, s) cB[((ch) * NPLANE + (pl)) * S + (s)]
   const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
-  // inside values of this cell (for the posteriors that are counted)
-  for (int s = lane; s < S; s += WARP_N) {
-    cA[PL_L * S + s] = t.aLl[il + s];
-    cA[PL_P * S + s] = gP ? t.aP[ir + s] : 0.;
-    cA[PL_2 * S + s] = gB ? t.a2[ir + s] : 0.;
-    cA[PL_M * S + s] = gM ? t.aM[il + s] : 0.;
-    cA[PL_E * S + s] = gE ? t.aE[il + s] : 0.;
-    for (int ch = 0; ch < NCH; ++ch) {
-      CB(ch, PL_E, s) = 0.; CB(ch, PL_M, s) = 0.; CB(ch, PL_1, s) = 0.; CB(ch, PL_B, s) = 0.;
-      CB(ch, PL_2, s) = 0.; CB(ch, PL_P, s) = 0.; CB(ch, PL_L, s) = 0.;
-    }
-  }
-  w_sync();
-  // ---- E(i,j,s1) <- parent P(i-1,j+1,s) (pair emission at i-1 and j)
+  double* cE = w.curB;  // [NCH][S] E of this cell
   if (gE) {
     const int xl = q.x[i - 1], xr = q.x[j];
     const double wsl = c.wsf[i - 1], wsr = c.wsf[j];
@@ -909,7 +947,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
       double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr);
       if (fl & 1) wt *= wsl;
       if (fl & 2) wt *= wsr;
-      double ac = cA[PL_E * S + s1];
+      double ac = t.aE[il + s1];
       for (int ch = 0; ch < NCH; ++ch) {
         double contrib = t.bP[ch * t.bch + pb + s] * wt;
         w.partA[ch * NM + pz] = contrib;
@@ -919,10 +957,14 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
     }
     w_sync();
     for (int s = lane; s < S; s += WARP_N)
-      for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_E, s) = seg_sum(w.partA + ch * NM, h.pT_off, s);
+      for (int ch = 0; ch < NCH; ++ch) {
+        double v = seg_sum(w.partA + ch * NM, h.pT_off, s);
+        cE[ch * S + s] = v;
+        t.bEl[ch * t.bch + il + s] = v;
+        t.bEr[ch * t.bch + ir + s] = v;
+      }
     w_sync();
   }
-  // ---- M(i,j,s) <- E(i,j,s) | parent M(i-1,j,sp) emitting x[i-1]
   if (gM) {
     bool cM = gE;
     double tM = 0., m0 = 1., m1 = 1.;
@@ -941,7 +983,7 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
         int sp = ld_ro(h.l_tgt + a), s1 = ld_ro(h.l_src + a);
         double wt = ld_ro(p.l_w + a * 5 + xl);
         if (ld_ro(h.l_flag + a) & 1) wt *= wsl;
-        double ac = cA[PL_M * S + s1];
+        double ac = t.aM[il + s1];
         for (int ch = 0; ch < NCH; ++ch) {
           double contrib = t.bM[ch * t.bch + pb + sp] * wt;
           w.partA[ch * NM + pz] = contrib;
@@ -952,344 +994,403 @@ template <int NCH> RDEV void lin_outside_cell(const LinCtx& c, const CTabs& t, i
     }
     for (int s = lane; s < S; s += WARP_N) {
       int sl = ld_ro(h.slot + s);
+      double am = cM ? t.aM[il + s] : 0.;
       for (int ch = 0; ch < NCH; ++ch) {
         double x = okM ? seg_sum(w.partA + ch * NM, h.lT_off, s) : 0.;
         if (cM) {
-          double y = CB(ch, PL_E, s) * (sl ? m1 : m0);
+          double y = cE[ch * S + s] * (sl ? m1 : m0);
           x += y;
-          eh.add(ch, sl, tM * y * cA[PL_M * S + s]);
+          eh.add(ch, sl, tM * y * am);
         }
-        CB(ch, PL_M, s) = x;
+        t.bM[ch * t.bch + il + s] = x;
       }
     }
     w_sync();
   }
-  if (gB) {
-    // ---- 1(i,j,sl): left child of B(i,j',s) with right sibling 2(j,j',sr)
-    {
-      int nk = 0;
-      const unsigned* ri = q.lf + i * q.mw;
-      const unsigned* rk = q.lf + j * q.mw;
-      int dmax = W < L - i ? W : L - i;
-      for (int d20 = d; d20 <= dmax; d20 += WARP_N) {
-        int d2 = d20 + lane;
-        bool ok = d2 <= dmax && row_bit(ri, d2) && row_bit(rk, d2 - d);
-        unsigned bal = w_ballot(ok);
-        if (ok) w.kbuf[nk + w_popc(bal & lanemask_lt())] = d2;
-        nk += w_popc(bal);
-      }
-      w_sync();
-      const unsigned rb = cidx(q, i, 0);
-      for (int pz = lane; pz < h.n_split; pz += WARP_N) {
-        int a = ld_ro(h.spL_ord + pz);
-        int s = ld_ro(h.sp_tgt + a), sr = ld_ro(h.sp_r + a);
-        double v[NCH];
-        for (int ch = 0; ch < NCH; ++ch) v[ch] = 0.;
-        for (int tt = 0; tt < nk; ++tt) {
-          int d2 = w.kbuf[tt];
-          double sib = t.a2[cidx(q, i + d2, d2 - d) + sr];
-          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBl[ch * t.bch + rb + (unsigned)d2 * S + s] * sib;
-        }
-        for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
-      }
-      w_sync();
-      for (int s = lane; s < S; s += WARP_N)
-        for (int ch = 0; ch < NCH; ++ch) {
-          double x = seg_sum(w.partA + ch * NM, h.spL_off, s);
-          CB(ch, PL_1, s) = x;
-          CB(ch, PL_B, s) = x + (gM ? CB(ch, PL_M, s) : 0.);
-        }
-      w_sync();
-    }
-    // ---- 2(i,j,sr): right child of B(i',j,s) with left sibling 1(i',i,sl); 1(i,j,sr); parent 2(i,j+1,sp) emitting x[j]
-    {
-      int nk = 0;
-      const unsigned* rj = c.lfr + j * q.mw;
-      int dmax = W < j ? W : j;
-      for (int d20 = d; d20 <= dmax; d20 += WARP_N) {
-        int d2 = d20 + lane;
-        bool ok = d2 <= dmax && row_bit(rj, d2) && row_bit(q.lf + (j - d2) * q.mw, d2 - d);
-        unsigned bal = w_ballot(ok);
-        if (ok) w.kbuf[nk + w_popc(bal & lanemask_lt())] = d2;
-        nk += w_popc(bal);
-      }
-      w_sync();
-      const unsigned rb = cidx(q, j, 0);
-      for (int pz = lane; pz < h.n_split; pz += WARP_N) {
-        int a = ld_ro(h.spR_ord + pz);
-        int s = ld_ro(h.sp_tgt + a), sl = ld_ro(h.sp_l + a);
-        double v[NCH];
-        for (int ch = 0; ch < NCH; ++ch) v[ch] = 0.;
-        for (int tt = 0; tt < nk; ++tt) {
-          int d2 = w.kbuf[tt];
-          double sib = t.a1[cidx(q, j - d2, d2 - d) + sl];
-          for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBr[ch * t.bch + rb + (unsigned)d2 * S + s] * sib;
-        }
-        for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
-      }
-      w_sync();
-      for (int s = lane; s < S; s += WARP_N)
-        for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_2, s) = seg_sum(w.partA + ch * NM, h.spR_off, s) + CB(ch, PL_1, s);
-      w_sync();
-      if (ok_B(q, i, d + 1)) {
-        const int xr = q.x[j];
-        const double wsr = c.wsf[j];
-        const unsigned pb = cidx(q, i, d + 1);
-        for (int pz = lane; pz < h.n_right; pz += WARP_N) {
-          int a = ld_ro(h.rT_ord + pz);
-          int sp = ld_ro(h.r_tgt + a), s1 = ld_ro(h.r_src + a);
-          double wt = ld_ro(p.r_w + a * 5 + xr);
-          if (ld_ro(h.r_flag + a) & 1) wt *= wsr;
-          double ac = cA[PL_2 * S + s1];
-          for (int ch = 0; ch < NCH; ++ch) {
-            double contrib = t.b2[ch * t.bch + pb + sp] * wt;
-            w.partA[ch * NM + pz] = contrib;
-            if (!p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
-          }
-        }
-        w_sync();
-        for (int s = lane; s < S; s += WARP_N)
-          for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_2, s) += seg_sum(w.partA + ch * NM, h.rT_off, s);
-        w_sync();
-      }
-    }
-  }
-  // ---- P(i,j,s1)
-  if (gP) {
-    // 2(i,j,s) <- P(i,j,s)
-    if (gB) {
-      bool c2P = true;
-      double tsc = 0., f0 = 1., f1 = 1.;
-      if (!ne) {
-        tsc = nl_e_ext(&q, i, j - 1, 0) + LC.en.mlintern;
-        c2P = tsc > NINF;
-        if (c2P) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
-      }
-      if (c2P)
-        for (int s = lane; s < S; s += WARP_N) {
-          int sl = ld_ro(h.slot + s);
-          for (int ch = 0; ch < NCH; ++ch) {
-            double y = CB(ch, PL_2, s) * (sl ? f1 : f0);
-            CB(ch, PL_P, s) += y;
-            eh.add(ch, sl, tsc * y * cA[PL_P * S + s]);
-          }
-        }
-      w_sync();
-    }
-    // parent P(i-1,j+1,s) stacking on this pair
-    if (ok_P(q, i - 1, d + 2)) {
-      bool cPP = true;
-      double tsc = 0., f0 = 1., f1 = 1.;
-      if (!ne) {
-        tsc = nl_e_loop(&q, i - 1, j, i, j - 1);
-        cPP = tsc > NINF;
-        if (cPP) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
-      }
-      if (cPP) {
-        const int xl = q.x[i - 1], xr = q.x[j];
-        const double wsl = c.wsf[i - 1], wsr = c.wsf[j];
-        const unsigned pb = cidx(q, i - 1, d + 2);
-        for (int pz = lane; pz < h.n_pair; pz += WARP_N) {
-          int a = ld_ro(h.pT_ord + pz);
-          int s = ld_ro(h.p_tgt + a), s1 = ld_ro(h.p_src + a), fl = ld_ro(h.p_flag + a);
-          int sl = ld_ro(h.slot + s);
-          double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr) * (sl ? f1 : f0);
-          if (fl & 1) wt *= wsl;
-          if (fl & 2) wt *= wsr;
-          double ac = cA[PL_P * S + s1];
-          for (int ch = 0; ch < NCH; ++ch) {
-            double contrib = t.bP[ch * t.bch + pb + s] * wt;
-            w.partA[ch * NM + pz] = contrib;
-            double post = contrib * ac;
-            eh.add(ch, sl, tsc * post);
-            if (!p.no_prf && post != 0.) sm_add(w.pcnt + (ch * h.n_pair + a) * 25 + xl * 5 + xr, post);
-          }
-        }
-        w_sync();
-        for (int s = lane; s < S; s += WARP_N)
-          for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_P, s) += seg_sum(w.partA + ch * NM, h.pT_off, s);
-        w_sync();
-      }
-    }
-    // exterior parent O(j,s) <- O(i,sl) P(i,j,sr)
-    {
-      bool cX = true;
-      double tsc = 0., f0 = 1., f1 = 1.;
-      if (!ne) {
-        tsc = nl_e_ext(&q, i, j - 1, 1);
-        cX = tsc > NINF;
-        if (cX) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
-      }
-      if (cX) {
-        for (int pz = lane; pz < h.n_split; pz += WARP_N) {
-          int a = ld_ro(h.spR_ord + pz);
-          int s = ld_ro(h.sp_tgt + a), sl_ = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
-          int sl = ld_ro(h.slot + s);
-          double term = t.aO[(unsigned)i * S + sl_] * (sl ? f1 : f0);
-          double ac = cA[PL_P * S + sr];
-          for (int ch = 0; ch < NCH; ++ch) {
-            double contrib = t.bO[ch * t.boch + (unsigned)j * S + s] * term;
-            w.partA[ch * NM + pz] = contrib;
-            eh.add(ch, sl, tsc * contrib * ac);
-          }
-        }
-        w_sync();
-        for (int s = lane; s < S; s += WARP_N)
-          for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_P, s) += seg_sum(w.partA + ch * NM, h.spR_off, s);
-        w_sync();
-      }
-    }
-    // enclosing interior loops E(i',j',s) <- P(i,j,s1) L(i',i,s2) L(j,j',s3)
-    if (h.n_quad > 0) {
-      for (int a = lane; a < h.n_quad; a += WARP_N)
-        for (int ch = 0; ch < NCH; ++ch) { w.partA[ch * NM + a] = 0.; w.partT[ch * NM + a] = 0.; }
-      w_sync();
-      walk_outer(c, i, d, w, [&](int n) {
-        for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
-          int a = ld_ro(h.qP_ord + pz);
-          int s = ld_ro(h.q_tgt + a), s2 = ld_ro(h.q_s2 + a), s3 = ld_ro(h.q_s3 + a);
-          const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
-          double v[NCH], vt[NCH];
-          for (int ch = 0; ch < NCH; ++ch) { v[ch] = w.partA[ch * NM + pz]; vt[ch] = w.partT[ch * NM + pz]; }
-          for (int pp = 0; pp < n; ++pp) {
-            int i2 = w.bi[pp], j2 = w.bj[pp];
-            double term = t.aLl[cidx(q, i2, i - i2) + s2] * t.aLr[cidx(q, j2, j2 - j) + s3] * bf[pp];
-            double tsc = w.bt[pp];
-            unsigned eb = cidx(q, i2, j2 - i2) + s;
-            for (int ch = 0; ch < NCH; ++ch) {
-              double x = t.bEl[ch * t.bch + eb] * term;
-              v[ch] += x;
-              vt[ch] += tsc * x;
-            }
-          }
-          for (int ch = 0; ch < NCH; ++ch) { w.partA[ch * NM + pz] = v[ch]; w.partT[ch * NM + pz] = vt[ch]; }
-        }
-      });
-      for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
-        int a = ld_ro(h.qP_ord + pz);
-        int sl = ld_ro(h.slot + ld_ro(h.q_tgt + a));
-        double ac = cA[PL_P * S + ld_ro(h.q_s1 + a)];
-        for (int ch = 0; ch < NCH; ++ch) eh.add(ch, sl, w.partT[ch * NM + pz] * ac);
-      }
-      for (int s = lane; s < S; s += WARP_N)
-        for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_P, s) += seg_sum(w.partA + ch * NM, h.qP_off, s);
-      w_sync();
-    }
-  }
-  // ---- L(i,j,s)
+}
+
+// ---- outside, phase B (cells with gB):
+//   1(i,j,sl): left child of B(i,j',s) with right sibling 2(j,j',sr);   B = 1 + M
+//   2(i,j,sr): right child of B(i',j,s) with left sibling 1(i',i,sl); + 1(i,j,sr); + parent 2(i,j+1,sp) emitting x[j]
+template <int NCH> RDEV void lin_out_B(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpLin& w) {
+  const LinHMM& h = LC.h;
+  const LinParams& p = LC.p;
+  const SeqView& q = c.q;
+  const int S = q.S, j = i + d, lane = lane_id(), L = q.L, W = q.W, NM = w.n_max;
+  const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
+  double* c1 = w.curB;  // [NCH][S] 1 of this cell
   {
-    // hairpin closed by (i-1,j): E(i,j,s) <- L(i,j,s)
-    if (gE) {
-      bool cH = true;
-      double tH = 0., h0 = 1., h1 = 1.;
-      if (!ne) {
-        tH = nl_e_hairpin(&q, i - 1, j);
-        cH = tH > NINF;
-        if (cH) { F2 ff = boltz2(tH); h0 = ff.f0; h1 = ff.f1; }
-      }
-      if (cH)
-        for (int s = lane; s < S; s += WARP_N) {
-          if (!ld_ro(h.is_loop + s)) continue;
-          int sl = ld_ro(h.slot + s);
-          for (int ch = 0; ch < NCH; ++ch) {
-            double y = CB(ch, PL_E, s) * (sl ? h1 : h0);
-            CB(ch, PL_L, s) += y;
-            eh.add(ch, sl, tH * y * cA[PL_L * S + s]);
-          }
-        }
-      w_sync();
+    int nk = 0;
+    const unsigned* ri = q.lf + i * q.mw;
+    const unsigned* rk = q.lf + j * q.mw;
+    int dmax = W < L - i ? W : L - i;
+    for (int d20 = d; d20 <= dmax; d20 += WARP_N) {
+      int d2 = d20 + lane;
+      bool ok = d2 <= dmax && row_bit(ri, d2) && row_bit(rk, d2 - d);
+      unsigned bal = w_ballot(ok);
+      if (ok) w.kbuf[nk + w_popc(bal & lanemask_lt())] = d2;
+      nk += w_popc(bal);
     }
-    // parent L(i,j+1,sp) emitting x[j]
-    if (d + 1 <= W && j + 1 <= L) {
+    w_sync();
+    // sibling 2(j, j') by right end: row i+d2, span d2-d -> offset ((i+d2)*W1 + d2-d)*S = base + d2*(W1+1)*S
+    const int sib0 = (i * q.W1 - d) * S, sstep = (q.W1 + 1) * S;
+    const unsigned rb = cidx(q, i, 0);
+    for (int pz = lane; pz < h.n_split; pz += WARP_N) {
+      int a = ld_ro(h.spL_ord + pz);
+      int s = ld_ro(h.sp_tgt + a), sr = ld_ro(h.sp_r + a);
+      double v[NCH];
+      for (int ch = 0; ch < NCH; ++ch) v[ch] = 0.;
+      for (int tt = 0; tt < nk; ++tt) {
+        int d2 = w.kbuf[tt];
+        double sib = t.a2[sib0 + d2 * sstep + sr];
+        for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBl[ch * t.bch + rb + (unsigned)d2 * S + s] * sib;
+      }
+      for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) {
+        double x = seg_sum(w.partA + ch * NM, h.spL_off, s);
+        c1[ch * S + s] = x;
+        double bb = x + (gM ? t.bM[ch * t.bch + il + s] : 0.);
+        t.bBl[ch * t.bch + il + s] = bb;
+        t.bBr[ch * t.bch + ir + s] = bb;
+      }
+    w_sync();
+  }
+  {
+    int nk = 0;
+    const unsigned* rj = c.lfr + j * q.mw;
+    int dmax = W < j ? W : j;
+    for (int d20 = d; d20 <= dmax; d20 += WARP_N) {
+      int d2 = d20 + lane;
+      bool ok = d2 <= dmax && row_bit(rj, d2) && row_bit(q.lf + (j - d2) * q.mw, d2 - d);
+      unsigned bal = w_ballot(ok);
+      if (ok) w.kbuf[nk + w_popc(bal & lanemask_lt())] = d2;
+      nk += w_popc(bal);
+    }
+    w_sync();
+    // sibling 1(i', i) by left end: row j-d2, span d2-d -> offset ((j-d2)*W1 + d2-d)*S = base - d2*(W1-1)*S
+    const int sib0 = (j * q.W1 - d) * S, sstep = (q.W1 - 1) * S;
+    const unsigned rb = cidx(q, j, 0);
+    for (int pz = lane; pz < h.n_split; pz += WARP_N) {
+      int a = ld_ro(h.spR_ord + pz);
+      int s = ld_ro(h.sp_tgt + a), sl = ld_ro(h.sp_l + a);
+      double v[NCH];
+      for (int ch = 0; ch < NCH; ++ch) v[ch] = 0.;
+      for (int tt = 0; tt < nk; ++tt) {
+        int d2 = w.kbuf[tt];
+        double sib = t.a1[sib0 - d2 * sstep + sl];
+        for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBr[ch * t.bch + rb + (unsigned)d2 * S + s] * sib;
+      }
+      for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) c1[ch * S + s] += seg_sum(w.partA + ch * NM, h.spR_off, s);
+    w_sync();
+    const bool okp = ok_B(q, i, d + 1);
+    if (okp) {
       const int xr = q.x[j];
       const double wsr = c.wsf[j];
       const unsigned pb = cidx(q, i, d + 1);
       for (int pz = lane; pz < h.n_right; pz += WARP_N) {
         int a = ld_ro(h.rT_ord + pz);
-        int fl = ld_ro(h.r_flag + a);
-        double contrib0 = 0.;
         int sp = ld_ro(h.r_tgt + a), s1 = ld_ro(h.r_src + a);
-        double wt = 0.;
-        if (fl & 2) {
-          wt = ld_ro(p.r_w + a * 5 + xr);
-          if (fl & 1) wt *= wsr;
-        }
-        double ac = cA[PL_L * S + s1];
+        double wt = ld_ro(p.r_w + a * 5 + xr);
+        if (ld_ro(h.r_flag + a) & 1) wt *= wsr;
+        double ac = t.a2[ir + s1];
         for (int ch = 0; ch < NCH; ++ch) {
-          double contrib = (fl & 2) ? t.bL[ch * t.bch + pb + sp] * wt : contrib0;
+          double contrib = t.b2[ch * t.bch + pb + sp] * wt;
           w.partA[ch * NM + pz] = contrib;
           if (!p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
         }
       }
       w_sync();
+    }
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) {
+        double x = c1[ch * S + s];
+        if (okp) x += seg_sum(w.partA + ch * NM, h.rT_off, s);
+        t.b2[ch * t.bch + il + s] = x;
+      }
+    w_sync();
+  }
+}
+
+// ---- outside, phase P (cells with an allowed pair)
+template <int NCH>
+RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, WarpLin& w, EhAcc<NCH>& eh) {
+  const LinHMM& h = LC.h;
+  const LinParams& p = LC.p;
+  const SeqView& q = c.q;
+  const int S = q.S, j = i + d, lane = lane_id(), NM = w.n_max;
+  const bool ne = LC.en.no_ene != 0;
+  const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
+  double* cP = w.curB;  // [NCH][S]
+  // 2(i,j,s) <- P(i,j,s)
+  {
+    bool c2P = gB;
+    double tsc = 0., f0 = 1., f1 = 1.;
+    if (gB && !ne) {
+      tsc = nl_e_ext(&q, i, j - 1, 0) + LC.en.mlintern;
+      c2P = tsc > NINF;
+      if (c2P) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
+    }
+    for (int s = lane; s < S; s += WARP_N) {
+      int sl = ld_ro(h.slot + s);
+      double ap = c2P ? t.aP[ir + s] : 0.;
+      for (int ch = 0; ch < NCH; ++ch) {
+        double y = 0.;
+        if (c2P) {
+          y = t.b2[ch * t.bch + il + s] * (sl ? f1 : f0);
+          eh.add(ch, sl, tsc * y * ap);
+        }
+        cP[ch * S + s] = y;
+      }
+    }
+    w_sync();
+  }
+  // parent P(i-1,j+1,s) stacking on this pair
+  if (ok_P(q, i - 1, d + 2)) {
+    bool cPP = true;
+    double tsc = 0., f0 = 1., f1 = 1.;
+    if (!ne) {
+      tsc = nl_e_loop(&q, i - 1, j, i, j - 1);
+      cPP = tsc > NINF;
+      if (cPP) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
+    }
+    if (cPP) {
+      const int xl = q.x[i - 1], xr = q.x[j];
+      const double wsl = c.wsf[i - 1], wsr = c.wsf[j];
+      const unsigned pb = cidx(q, i - 1, d + 2);
+      for (int pz = lane; pz < h.n_pair; pz += WARP_N) {
+        int a = ld_ro(h.pT_ord + pz);
+        int s = ld_ro(h.p_tgt + a), s1 = ld_ro(h.p_src + a), fl = ld_ro(h.p_flag + a);
+        int sl = ld_ro(h.slot + s);
+        double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr) * (sl ? f1 : f0);
+        if (fl & 1) wt *= wsl;
+        if (fl & 2) wt *= wsr;
+        double ac = t.aP[ir + s1];
+        for (int ch = 0; ch < NCH; ++ch) {
+          double contrib = t.bP[ch * t.bch + pb + s] * wt;
+          w.partA[ch * NM + pz] = contrib;
+          double post = contrib * ac;
+          eh.add(ch, sl, tsc * post);
+          if (!p.no_prf && post != 0.) sm_add(w.pcnt + (ch * h.n_pair + a) * 25 + xl * 5 + xr, post);
+        }
+      }
+      w_sync();
       for (int s = lane; s < S; s += WARP_N)
-        for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_L, s) += seg_sum(w.partA + ch * NM, h.rT_off, s);
+        for (int ch = 0; ch < NCH; ++ch) cP[ch * S + s] += seg_sum(w.partA + ch * NM, h.pT_off, s);
       w_sync();
     }
-    // unpaired flanks of interior loops
-    if (d >= 1 && d <= c.Ceff && h.n_quad > 0) {
-      if (i >= 1) {
-        for (int a = lane; a < h.n_quad; a += WARP_N)
-          for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
-        w_sync();
-        const unsigned eb = cidx(q, i, 0);
-        walk_left_flank(c, i, d, w, [&](int n) {
-          for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
-            int a = ld_ro(h.qL_ord + pz);
-            int s = ld_ro(h.q_tgt + a), s1 = ld_ro(h.q_s1 + a), s3 = ld_ro(h.q_s3 + a);
-            const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
-            double v[NCH];
-            for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
-            for (int pp = 0; pp < n; ++pp) {
-              int l = w.bi[pp], j2 = w.bj[pp];
-              double term = t.aP[cidx(q, l, l - j) + s1] * t.aLr[cidx(q, j2, j2 - l) + s3] * bf[pp];
-              for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEl[ch * t.bch + eb + (unsigned)(j2 - i) * S + s] * term;
-            }
-            for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
-          }
-        });
-        for (int s = lane; s < S; s += WARP_N)
-          for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_L, s) += seg_sum(w.partA + ch * NM, h.qL_off, s);
-        w_sync();
+  }
+  // exterior parent O(j,s) <- O(i,sl) P(i,j,sr)
+  {
+    bool cX = true;
+    double tsc = 0., f0 = 1., f1 = 1.;
+    if (!ne) {
+      tsc = nl_e_ext(&q, i, j - 1, 1);
+      cX = tsc > NINF;
+      if (cX) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
+    }
+    if (cX) {
+      for (int pz = lane; pz < h.n_split; pz += WARP_N) {
+        int a = ld_ro(h.spR_ord + pz);
+        int s = ld_ro(h.sp_tgt + a), sl_ = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
+        int sl = ld_ro(h.slot + s);
+        double term = t.aO[(unsigned)i * S + sl_] * (sl ? f1 : f0);
+        double ac = t.aP[ir + sr];
+        for (int ch = 0; ch < NCH; ++ch) {
+          double contrib = t.bO[ch * t.boch + (unsigned)j * S + s] * term;
+          w.partA[ch * NM + pz] = contrib;
+          eh.add(ch, sl, tsc * contrib * ac);
+        }
       }
-      if (j + 1 <= L) {
-        for (int a = lane; a < h.n_quad; a += WARP_N)
-          for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
-        w_sync();
-        const unsigned eb = cidx(q, j, 0);
-        walk_right_flank(c, i, d, w, [&](int n) {
-          for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
-            int a = ld_ro(h.qR_ord + pz);
-            int s = ld_ro(h.q_tgt + a), s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a);
-            const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
-            double v[NCH];
-            for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
-            for (int pp = 0; pp < n; ++pp) {
-              int k = w.bi[pp], i2 = w.bj[pp];
-              double term = t.aP[cidx(q, i, i - k) + s1] * t.aLl[cidx(q, i2, k - i2) + s2] * bf[pp];
-              for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEr[ch * t.bch + eb + (unsigned)(j - i2) * S + s] * term;
-            }
-            for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
-          }
-        });
-        for (int s = lane; s < S; s += WARP_N)
-          for (int ch = 0; ch < NCH; ++ch) CB(ch, PL_L, s) += seg_sum(w.partA + ch * NM, h.qR_off, s);
-        w_sync();
-      }
+      w_sync();
+      for (int s = lane; s < S; s += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) cP[ch * S + s] += seg_sum(w.partA + ch * NM, h.spR_off, s);
+      w_sync();
     }
   }
-  // ---- write back
-  for (int s = lane; s < S; s += WARP_N)
-    for (int ch = 0; ch < NCH; ++ch) {
-      const unsigned o = ch * t.bch;
-      if (d >= 1) t.bL[o + il + s] = CB(ch, PL_L, s);
-      if (gP) t.bP[o + il + s] = CB(ch, PL_P, s);
-      if (gE) { t.bEl[o + il + s] = CB(ch, PL_E, s); t.bEr[o + ir + s] = CB(ch, PL_E, s); }
-      if (gM) t.bM[o + il + s] = CB(ch, PL_M, s);
-      if (gB) { t.bBl[o + il + s] = CB(ch, PL_B, s); t.bBr[o + ir + s] = CB(ch, PL_B, s); t.b2[o + il + s] = CB(ch, PL_2, s); }
+  // enclosing interior loops E(i',j',s) <- P(i,j,s1) L(i',i,s2) L(j,j',s3)
+  if (h.n_quad > 0) {
+    for (int a = lane; a < h.n_quad; a += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) { w.partA[ch * NM + a] = 0.; w.partT[ch * NM + a] = 0.; }
+    w_sync();
+    walk_outer(c, i, d, w, [&](int n) {
+      for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
+        int a = ld_ro(h.qP_ord + pz);
+        int s = ld_ro(h.q_tgt + a), s2 = ld_ro(h.q_s2 + a), s3 = ld_ro(h.q_s3 + a);
+        const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
+        double v[NCH], vt[NCH];
+        for (int ch = 0; ch < NCH; ++ch) { v[ch] = w.partA[ch * NM + pz]; vt[ch] = w.partT[ch * NM + pz]; }
+        for (int pp = 0; pp < n; ++pp) {
+          int i2 = w.bi[pp], j2 = w.bj[pp];
+          double term = t.aLl[cidx(q, i2, i - i2) + s2] * t.aLr[cidx(q, j2, j2 - j) + s3] * bf[pp];
+          double tsc = w.bt[pp];
+          unsigned eb = cidx(q, i2, j2 - i2) + s;
+          for (int ch = 0; ch < NCH; ++ch) {
+            double x = t.bEl[ch * t.bch + eb] * term;
+            v[ch] += x;
+            vt[ch] += tsc * x;
+          }
+        }
+        for (int ch = 0; ch < NCH; ++ch) { w.partA[ch * NM + pz] = v[ch]; w.partT[ch * NM + pz] = vt[ch]; }
+      }
+    });
+    for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
+      int a = ld_ro(h.qP_ord + pz);
+      int sl = ld_ro(h.slot + ld_ro(h.q_tgt + a));
+      double ac = t.aP[ir + ld_ro(h.q_s1 + a)];
+      for (int ch = 0; ch < NCH; ++ch) eh.add(ch, sl, w.partT[ch * NM + pz] * ac);
     }
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) cP[ch * S + s] += seg_sum(w.partA + ch * NM, h.qP_off, s);
+    w_sync();
+  }
+  for (int s = lane; s < S; s += WARP_N)
+    for (int ch = 0; ch < NCH; ++ch) t.bP[ch * t.bch + il + s] = cP[ch * S + s];
   w_sync();
-#undef CB
+}
+
+// ---- outside, phase L (every cell): hairpin E(i,j,s) <- L(i,j,s); parent L(i,j+1,sp) emitting x[j]; unpaired flanks
+template <int NCH>
+RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, WarpLin& w, EhAcc<NCH>& eh) {
+  const LinHMM& h = LC.h;
+  const LinParams& p = LC.p;
+  const SeqView& q = c.q;
+  const int S = q.S, j = i + d, lane = lane_id(), L = q.L, W = q.W, NM = w.n_max;
+  const bool ne = LC.en.no_ene != 0;
+  const unsigned il = cidx(q, i, d);
+  double* cL = w.curB;  // [NCH][S]
+  {
+    bool cH = gE;
+    double tH = 0., h0 = 1., h1 = 1.;
+    if (gE && !ne) {
+      tH = nl_e_hairpin(&q, i - 1, j);
+      cH = tH > NINF;
+      if (cH) { F2 ff = boltz2(tH); h0 = ff.f0; h1 = ff.f1; }
+    }
+    for (int s = lane; s < S; s += WARP_N) {
+      int sl = ld_ro(h.slot + s);
+      bool use = cH && ld_ro(h.is_loop + s);
+      double al = use ? t.aLl[il + s] : 0.;
+      for (int ch = 0; ch < NCH; ++ch) {
+        double y = 0.;
+        if (use) {
+          y = t.bEl[ch * t.bch + il + s] * (sl ? h1 : h0);
+          eh.add(ch, sl, tH * y * al);
+        }
+        cL[ch * S + s] = y;
+      }
+    }
+    w_sync();
+  }
+  if (d + 1 <= W && j + 1 <= L) {
+    const int xr = q.x[j];
+    const double wsr = c.wsf[j];
+    const unsigned pb = cidx(q, i, d + 1);
+    for (int pz = lane; pz < h.n_right; pz += WARP_N) {
+      int a = ld_ro(h.rT_ord + pz);
+      int fl = ld_ro(h.r_flag + a);
+      int sp = ld_ro(h.r_tgt + a), s1 = ld_ro(h.r_src + a);
+      double wt = 0.;
+      if (fl & 2) {
+        wt = ld_ro(p.r_w + a * 5 + xr);
+        if (fl & 1) wt *= wsr;
+      }
+      double ac = t.aLl[il + s1];
+      for (int ch = 0; ch < NCH; ++ch) {
+        double contrib = (fl & 2) ? t.bL[ch * t.bch + pb + sp] * wt : 0.;
+        w.partA[ch * NM + pz] = contrib;
+        if (!p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
+      }
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) cL[ch * S + s] += seg_sum(w.partA + ch * NM, h.rT_off, s);
+    w_sync();
+  }
+  if (d >= 1 && d <= c.Ceff && h.n_quad > 0) {
+    if (i >= 1) {
+      for (int a = lane; a < h.n_quad; a += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
+      w_sync();
+      const unsigned eb = cidx(q, i, 0);
+      bool any = false;
+      walk_left_flank(c, i, d, w, [&](int n) {
+        any = true;
+        for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
+          int a = ld_ro(h.qL_ord + pz);
+          int s = ld_ro(h.q_tgt + a), s1 = ld_ro(h.q_s1 + a), s3 = ld_ro(h.q_s3 + a);
+          const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
+          double v[NCH];
+          for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
+          for (int pp = 0; pp < n; ++pp) {
+            int l = w.bi[pp], j2 = w.bj[pp];
+            double term = t.aP[cidx(q, l, l - j) + s1] * t.aLr[cidx(q, j2, j2 - l) + s3] * bf[pp];
+            for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEl[ch * t.bch + eb + (unsigned)(j2 - i) * S + s] * term;
+          }
+          for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+        }
+      });
+      if (any)
+        for (int s = lane; s < S; s += WARP_N)
+          for (int ch = 0; ch < NCH; ++ch) cL[ch * S + s] += seg_sum(w.partA + ch * NM, h.qL_off, s);
+      w_sync();
+    }
+    if (j + 1 <= L) {
+      for (int a = lane; a < h.n_quad; a += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
+      w_sync();
+      const unsigned eb = cidx(q, j, 0);
+      bool any = false;
+      walk_right_flank(c, i, d, w, [&](int n) {
+        any = true;
+        for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
+          int a = ld_ro(h.qR_ord + pz);
+          int s = ld_ro(h.q_tgt + a), s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a);
+          const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
+          double v[NCH];
+          for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
+          for (int pp = 0; pp < n; ++pp) {
+            int k = w.bi[pp], i2 = w.bj[pp];
+            double term = t.aP[cidx(q, i, i - k) + s1] * t.aLl[cidx(q, i2, k - i2) + s2] * bf[pp];
+            for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEr[ch * t.bch + eb + (unsigned)(j - i2) * S + s] * term;
+          }
+          for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+        }
+      });
+      if (any)
+        for (int s = lane; s < S; s += WARP_N)
+          for (int ch = 0; ch < NCH; ++ch) cL[ch * S + s] += seg_sum(w.partA + ch * NM, h.qR_off, s);
+      w_sync();
+    }
+  }
+  if (d >= 1)
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) t.bL[ch * t.bch + il + s] = cL[ch * S + s];
+  w_sync();
+}
+
+// one diagonal of the outside pass, phase-major over the warp's cells
+template <int NCH> RDEV void lin_outside_diag(const LinCtx& c, const CTabs& t, int d, WarpLin& w, EhAcc<NCH>& eh) {
+  const SeqView& q = c.q;
+  const int ncell = q.L + 1 - d, w0 = warp_id(), nw = n_warps();
+  if (d >= 3)
+    for (int i = w0; i < ncell; i += nw) {
+      bool gE = ok_E(q, i, d), gM = ok_M(q, i, d);
+      if (gE || gM) lin_out_EM<NCH>(c, t, i, d, gE, gM, w, eh);
+    }
+  if (d >= q.min_pair) {
+    for (int i = w0; i < ncell; i += nw)
+      if (ok_B(q, i, d)) lin_out_B<NCH>(c, t, i, d, ok_M(q, i, d), w);
+    for (int i = w0; i < ncell; i += nw)
+      if (ok_P(q, i, d)) lin_out_P<NCH>(c, t, i, d, ok_B(q, i, d), w, eh);
+  }
+  for (int i = w0; i < ncell; i += nw) lin_out_L<NCH>(c, t, i, d, d >= 3 && ok_E(q, i, d), w, eh);
 }
 
 }  // namespace lin

@@ -28,7 +28,7 @@ namespace relem {
 namespace lin {
 using namespace relem::dp;
 
-#define LIN_THREADS 256
+#define LIN_THREADS 128
 
 struct LinLayout {
   unsigned long long stride;  // doubles per slot
@@ -79,8 +79,8 @@ static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int n_
   lay.sm_eh = sm(8 * 8);
   lay.sm_pcnt = sm(nch * h.n_pair * 25 * 8 + 8);
   lay.sm_warp = b;
-  lay.warp_bytes_in = warp_lin_bytes(h.S, Wmax, 1, h.n_max, 0, 0);
-  lay.warp_bytes_out = warp_lin_bytes(h.S, Wmax, nch, h.n_max, h.n_right, h.n_left);
+  lay.warp_bytes_in = warp_lin_bytes(h.S, Wmax, 1, h.n_max, 0, 0, true);
+  lay.warp_bytes_out = warp_lin_bytes(h.S, Wmax, nch, h.n_max, h.n_right, h.n_left, false);
   lay.sm_total_in = lay.sm_warp + lay.warp_bytes_in * nwarps;
   lay.sm_total_out = lay.sm_warp + lay.warp_bytes_out * nwarps;
   return lay;
@@ -187,7 +187,7 @@ RDEV void lin_load_masks(const LinKArgs& a, unsigned char* smem_raw, const LinCt
 
 // ------------------------------------------------------------------------------------------------ kernel A
 // energy-only inside/outside -> filtered base-pair masks of every sequence of the chunk
-LIN_KERNEL(3) relem_lin_filter_kernel(LinKArgs a LIN_SMEM_ARG) {
+LIN_KERNEL(8) relem_lin_filter_kernel(LinKArgs a LIN_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
@@ -270,7 +270,7 @@ RDEV CTabs lin_tabs(const LinLayout& lay, double* slot) {
 
 // ------------------------------------------------------------------------------------------------ kernel B
 // coupled inside pass + partition functions
-LIN_KERNEL(2) relem_lin_inside_kernel(LinKArgs a LIN_SMEM_ARG) {
+LIN_KERNEL(5) relem_lin_inside_kernel(LinKArgs a LIN_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
@@ -286,9 +286,9 @@ LIN_KERNEL(2) relem_lin_inside_kernel(LinKArgs a LIN_SMEM_ARG) {
   const LinHMM& h = LC.h;
   const int L = q.L, W = q.W, S = q.S;
   int* ctr = (int*)(smem_raw + lay.sm_ctr);
-  WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + warp_id() * lay.warp_bytes_in, S, lay.Wmax, 1, h.n_max, 0, 0);
+  WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + warp_id() * lay.warp_bytes_in, S, lay.Wmax, 1, h.n_max, 0, 0, true);
   CTabs t = lin_tabs(lay, slot);
-  for (int d = 0; d <= W; ++d) lin_diagonal(L + 1 - d, d, ctr, [&](int i) { lin_inside_cell(c, t, i, d, w); });
+  for (int d = 0; d <= W; ++d) { lin_inside_diag(c, t, d, w); CTA_SYNC(); }
   if (warp_id() == 0) lin_inside_ext(c, t, w);
   CTA_SYNC();
   if (CTA_TID == 0) {
@@ -313,7 +313,7 @@ LIN_KERNEL(2) relem_lin_inside_kernel(LinKArgs a LIN_SMEM_ARG) {
 
 // ------------------------------------------------------------------------------------------------ kernel C
 // coupled outside pass in gather form + expected counts
-template <int NCH> LIN_KERNEL(2) relem_lin_outside_kernel(LinKArgs a LIN_SMEM_ARG) {
+template <int NCH> LIN_KERNEL(5) relem_lin_outside_kernel(LinKArgs a LIN_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
@@ -333,7 +333,7 @@ template <int NCH> LIN_KERNEL(2) relem_lin_outside_kernel(LinKArgs a LIN_SMEM_AR
   double* seh = (double*)(smem_raw + lay.sm_eh);
   double* pcnt = (double*)(smem_raw + lay.sm_pcnt);
   WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + warp_id() * lay.warp_bytes_out, S, lay.Wmax, NCH, h.n_max,
-                             h.n_right, h.n_left);
+                             h.n_right, h.n_left, false);
   w.pcnt = pcnt;
   CTabs t = lin_tabs(lay, slot);
   const double Ztt = slot[lay.hdr + 0], Ztf = slot[lay.hdr + 1], Zft = slot[lay.hdr + 2];
@@ -370,7 +370,7 @@ template <int NCH> LIN_KERNEL(2) relem_lin_outside_kernel(LinKArgs a LIN_SMEM_AR
   for (int k = 0; k < NCH * 2; ++k) eh.v[k] = 0.;
   if (warp_id() == 0) lin_outside_ext<NCH>(c, t, w);
   CTA_SYNC();
-  for (int d = W; d >= 0; --d) lin_diagonal(L + 1 - d, d, ctr, [&](int i) { lin_outside_cell<NCH>(c, t, i, d, w, eh); });
+  for (int d = W; d >= 0; --d) { lin_outside_diag<NCH>(c, t, d, w, eh); CTA_SYNC(); }
   // ---- fold the per-entry emission sums into theta-shaped counts
   w_sync();
   if (!LC.p.no_prf) {
