@@ -1,11 +1,18 @@
-// relem_lin.cu -- persistent E-step kernel of the scaled linear-space path (dp_lin.cuh) and its launcher.
+// relem_lin.cu -- kernels and launcher of the scaled linear-space E-step (dp_lin.cuh).
 //
-// One CTA per resident sequence ("slot"), sequences claimed longest-first from an atomic queue.  Per sequence:
-//   1. set-up: bases, exp(position weights), special-hairpin hits, canonical-pair masks in both orientations;
-//   2. energy-only inside + outside in gather form -> base-pair posteriors -> bp_ok / left_bp_ok masks
-//      (EnergyModel::fill_bpp_tables, energy_model.hpp:211-266);
-//   3. coupled inside (wavefront over the span, warp per cell), exterior row, partition functions;
-//   4. coupled outside in gather form with the expected counts (RNAelemTrainDP, motif_trainer.hpp:204-245).
+// Execution model: WAVEFRONT ACROSS THE BATCH.  A chunk of sequences (as many as the scratch memory holds) is swept
+// span by span; for every span d and every phase of the cell update one small kernel is launched whose grid covers
+// (sequence, tile of cells on diagonal d) pairs, one warp per cell.  Kernel boundaries are the wavefront barriers.
+// Why not one persistent CTA per sequence (the first version of this file): the complete cell update is ~12K SASS
+// instructions, the SM's instruction cache holds ~2K, and ncu showed 2/3 of all stall samples as "no instruction"
+// (profiles/r1_lin_persistent.md).  One phase is a few hundred instructions, every warp on the GPU runs the same
+// phase at the same time, load balance is global instead of per CTA, and no intra-CTA barrier is left.
+//
+// Per chunk:  prep -> [energy-only inside d=3..W, exterior, exterior-outside, outside d=W..3, filter]
+//             -> coupled inside d=0..W (phases L,P,B,E) -> exterior + Z -> exterior-outside
+//             -> coupled outside d=W..0 (phases EM,B,P,L) -> fold counts.
+// Per-sequence data (bases, weights, masks, accumulators) lives in a header in the sequence's scratch slot.
+//
 // Built by nvcc for sm_100a (FMA contraction allowed: nothing here has to be bit-exact) and, with
 // -DRELEM_HOST_EMU under g++, into the single-threaded debug emulation used by the CPU tests.
 #include <algorithm>
@@ -29,23 +36,30 @@ namespace lin {
 using namespace relem::dp;
 
 #define LIN_THREADS 128
+#define LIN_WARPS (LIN_THREADS / 32)
 
 struct LinLayout {
   unsigned long long stride;  // doubles per slot
   unsigned long long aP, aE, aM, a1, a2, aLl, aLr, aO;
   unsigned long long bP, bEl, bEr, bM, bBl, bBr, b2, bL, bO, bch, boch;
   unsigned long long kP, kE, kM, k1, k2, kO, kbP, kbE, kbM, kbBl, kbBr, kb2, kbO;
-  unsigned long long hdr, masks;  // per-slot header: Z^tt, Z^tf, Z^ft, bad; filtered bp / lf bit rows
-  int Lmax, Wmax, mw;
-  int sm_ctx, sm_x, sm_sp3, sm_sp4, sm_sp6, sm_bp, sm_lf, sm_bpr, sm_lfr, sm_wsf, sm_k0pow, sm_red, sm_ctr, sm_total_k0;
-  int sm_en, sm_eh, sm_pcnt, sm_warp, warp_bytes_in, warp_bytes_out, sm_total_in, sm_total_out;
+  // per-slot header
+  unsigned long long hdr;    // [16]: Z^tt, Z^tf, Z^ft, bad, canonical pair count, -, -, -, EH[nch*2]
+  unsigned long long wsf;    // [Lmax+1] exp(position weight)
+  unsigned long long cnt;    // [nch][ncnt] emission posterior sums per (list entry, base)
+  unsigned long long masks;  // 4 x (Lmax+2)*mw words: bp, lf, bpr, lfr
+  unsigned long long bytes;  // x [Lmax+2], sp3, sp4, sp6 [Lmax+1 each]
+  int Lmax, Wmax, mw, nch, ncnt, mask_words;
+  int sm_ctx, sm_misc, sm_pcnt, sm_warp, warp_bytes_in, warp_bytes_out;
 };
 
-static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int n_theta, int nch, int nwarps) {
+static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int nch) {
   LinLayout lay;
   std::memset(&lay, 0, sizeof(lay));
   int Wmax = Lmax < max_span ? Lmax : max_span;
-  lay.Lmax = Lmax; lay.Wmax = Wmax; lay.mw = (Wmax + 1 + 31) / 32;
+  lay.Lmax = Lmax; lay.Wmax = Wmax; lay.mw = (Wmax + 1 + 31) / 32; lay.nch = nch;
+  lay.ncnt = 5 * h.n_right + 5 * h.n_left + 25 * h.n_pair;
+  lay.mask_words = (Lmax + 2) * lay.mw;
   unsigned long long cells = (unsigned long long)(Lmax + 1) * (Wmax + 1);
   unsigned long long band = cells * h.S, ext = (unsigned long long)(Lmax + 1) * h.S;
   unsigned long long o = 0;
@@ -60,37 +74,31 @@ static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int n_
   lay.kO = take(Lmax + 1);
   lay.kbP = take(cells); lay.kbE = take(cells); lay.kbM = take(cells); lay.kbBl = take(cells); lay.kbBr = take(cells);
   lay.kb2 = take(cells); lay.kbO = take(Lmax + 1);
-  lay.hdr = take(8);
-  lay.masks = take((unsigned long long)(Lmax + 2) * lay.mw);  // 2 masks x 4-byte words
+  lay.hdr = take(16);
+  lay.wsf = take(Lmax + 1);
+  lay.cnt = take((unsigned long long)nch * lay.ncnt);
+  lay.masks = take(2ull * lay.mask_words);
+  lay.bytes = take((4ull * (Lmax + 2) + 7) / 8);
   lay.stride = o;
   int b = 0;
   auto sm = [&](int bytes) { int r = b; b += (bytes + 15) & ~15; return r; };
   lay.sm_ctx = sm((int)sizeof(LinCtx));
-  lay.sm_x = sm(Lmax + 2);
-  lay.sm_sp3 = sm(Lmax + 1); lay.sm_sp4 = sm(Lmax + 1); lay.sm_sp6 = sm(Lmax + 1);
-  int mask_bytes = (Lmax + 2) * lay.mw * 4;
-  lay.sm_bp = sm(mask_bytes); lay.sm_lf = sm(mask_bytes); lay.sm_bpr = sm(mask_bytes); lay.sm_lfr = sm(mask_bytes);
-  lay.sm_wsf = sm((Lmax + 1) * 8);
-  lay.sm_k0pow = sm((Wmax + 3) * 8);
-  lay.sm_red = sm(64 * 8);
-  lay.sm_ctr = sm(16);
-  lay.sm_total_k0 = b;
-  lay.sm_en = sm(nch * n_theta * 8 + 8);
-  lay.sm_eh = sm(8 * 8);
+  lay.sm_misc = sm(64);
   lay.sm_pcnt = sm(nch * h.n_pair * 25 * 8 + 8);
   lay.sm_warp = b;
   lay.warp_bytes_in = warp_lin_bytes(h.S, Wmax, 1, h.n_max, 0, 0, true);
   lay.warp_bytes_out = warp_lin_bytes(h.S, Wmax, nch, h.n_max, h.n_right, h.n_left, false);
-  lay.sm_total_in = lay.sm_warp + lay.warp_bytes_in * nwarps;
-  lay.sm_total_out = lay.sm_warp + lay.warp_bytes_out * nwarps;
   return lay;
 }
 
 struct LinKArgs {
   BatchView b;
-  int base, count;   // this launch handles sequences order[base .. base+count), CTA k <-> slot k
+  int base, count;   // this chunk handles sequences order[base .. base+count), slot k <-> sequence base+k
+  int d;             // diagonal of a phase kernel
+  int tile, ntile;   // cells per CTA and CTAs per sequence of a phase kernel
   LinLayout lay;
   double* scratch;
+  const double* k0pow;
   EstepOut out;
   unsigned char* flag;
 };
@@ -109,153 +117,48 @@ RDEV void cta_right_mask(const SeqView& q, const unsigned* byleft, unsigned* byr
   }
 }
 
-// run `cell(i)` for every cell of diagonal d, cells handed to warps through a shared counter
-template <class F> RDEV void lin_diagonal(int ncell, int d, int* ctr, F cell) {
-  int* c = ctr + (d & 1);
-  if (CTA_TID == 0) ctr[(d + 1) & 1] = 0;
-  for (;;) {
-    int i = 0;
-    if (lane_id() == 0) i = ctr_next(c);
-    i = w_shfl(i, 0);
-    if (i >= ncell) break;
-    cell(i);
-  }
-  CTA_SYNC();
-}
-
 #ifdef RELEM_HOST_EMU
-#define LIN_KERNEL(MINB) inline void
+#define LIN_KERNEL(T, MINB) inline void
 #define LIN_SMEM_ARG , unsigned char* smem_raw, int emu_block
 #define LIN_BLOCK_IDX emu_block
+#define LIN_SHARED static
 #else
-#define LIN_KERNEL(MINB) __global__ void __launch_bounds__(LIN_THREADS, MINB)
+#define LIN_KERNEL(T, MINB) __global__ void __launch_bounds__(T, MINB)
 #define LIN_SMEM_ARG
 #define LIN_BLOCK_IDX ((int)blockIdx.x)
+#define LIN_SHARED __shared__
 #endif
 
 RDEV bool finite_pos(double v) { return v > 0. && v < (-NINF); }
 
-// per-sequence set-up common to the three kernels: the CTA's LinCtx (in shared memory), bases, exp(position weights),
-// special hairpins.  Returns the context; masks are filled by the caller.
-RDEV LinCtx& lin_setup(const LinKArgs& a, unsigned char* smem_raw, int n) {
+// the CTA's view of sequence slot `sk`: LinCtx in shared memory pointing at the slot header
+RDEV LinCtx& lin_attach(const LinKArgs& a, unsigned char* smem_raw, int sk, double*& slot, int& n) {
   const LinLayout& lay = a.lay;
   LinCtx& c = *(LinCtx*)(smem_raw + lay.sm_ctx);
-  unsigned char* sx = smem_raw + lay.sm_x;
-  double* wsf = (double*)(smem_raw + lay.sm_wsf);
-  double* k0pow = (double*)(smem_raw + lay.sm_k0pow);
-  const long long o = a.b.off[n];
-  const int L = (int)(a.b.off[n + 1] - o);
+  slot = a.scratch + (unsigned long long)sk * lay.stride;
+  n = a.b.order[a.base + sk];
   if (CTA_TID == 0) {
+    const long long o = a.b.off[n];
+    const int L = (int)(a.b.off[n + 1] - o);
     const int W = L < LC.en.max_span ? L : LC.en.max_span;
     const int C = W - 7 < LC.en.max_iloop ? W - 7 : LC.en.max_iloop;
     SeqView& q = c.q;
     q.L = L; q.W = W; q.C = C; q.W1 = W + 1; q.S = LC.h.S; q.cells = (unsigned)(L + 1) * (unsigned)(W + 1);
     q.mw = lay.mw; q.min_pair = 5; q.min_multi = 10;
-    q.x = sx;
-    q.bp = (unsigned*)(smem_raw + lay.sm_bp); q.lf = (unsigned*)(smem_raw + lay.sm_lf);
-    q.sp3 = (signed char*)(smem_raw + lay.sm_sp3); q.sp4 = (signed char*)(smem_raw + lay.sm_sp4);
-    q.sp6 = (signed char*)(smem_raw + lay.sm_sp6);
+    unsigned char* by = (unsigned char*)(slot + lay.bytes);
+    q.x = by;
+    q.sp3 = (signed char*)(by + (lay.Lmax + 2));
+    q.sp4 = (signed char*)(by + (lay.Lmax + 2) + (lay.Lmax + 1));
+    q.sp6 = (signed char*)(by + (lay.Lmax + 2) + 2 * (lay.Lmax + 1));
+    unsigned* mk = (unsigned*)(slot + lay.masks);
+    q.bp = mk; q.lf = mk + lay.mask_words;
+    c.bpr = mk + 2 * lay.mask_words; c.lfr = mk + 3 * lay.mask_words;
     q.ws = a.b.ws + o; q.emit0 = nullptr; q.emitT = nullptr;
-    c.bpr = (unsigned*)(smem_raw + lay.sm_bpr); c.lfr = (unsigned*)(smem_raw + lay.sm_lfr);
-    c.wsf = wsf; c.k0pow = k0pow;
+    c.wsf = slot + lay.wsf; c.k0pow = a.k0pow;
     c.Ceff = C < 30 ? C : 30;
-    sx[L] = 0; sx[L + 1] = 0;
-    int* ctr = (int*)(smem_raw + lay.sm_ctr);
-    ctr[0] = 0; ctr[1] = 0;
   }
-  for (int t = CTA_TID; t < L; t += CTA_NTH) { sx[t] = a.b.seq[o + t]; wsf[t] = exp(a.b.ws[o + t]); }
-  CTA_SYNC();
-  for (int t = CTA_TID; t <= c.q.W + 2; t += CTA_NTH) k0pow[t] = pow(LC.k0, (double)t);
-  cta_special_hairpins(LC.en, sx, L, (signed char*)(smem_raw + lay.sm_sp3), (signed char*)(smem_raw + lay.sm_sp4),
-                       (signed char*)(smem_raw + lay.sm_sp6));
   CTA_SYNC();
   return c;
-}
-// filtered masks of this slot (written by the filter kernel) -> shared memory, both orientations
-RDEV void lin_load_masks(const LinKArgs& a, unsigned char* smem_raw, const LinCtx& c, const double* slot) {
-  const LinLayout& lay = a.lay;
-  const unsigned* g = (const unsigned*)(slot + lay.masks);
-  unsigned* bp = (unsigned*)(smem_raw + lay.sm_bp);
-  unsigned* lf = (unsigned*)(smem_raw + lay.sm_lf);
-  const int nw = (c.q.L + 1) * lay.mw;
-  for (int t = CTA_TID; t < nw; t += CTA_NTH) { bp[t] = g[t]; lf[t] = g[nw + t]; }
-  CTA_SYNC();
-  cta_right_mask(c.q, bp, (unsigned*)(smem_raw + lay.sm_bpr));
-  cta_right_mask(c.q, lf, (unsigned*)(smem_raw + lay.sm_lfr));
-  CTA_SYNC();
-}
-
-// ------------------------------------------------------------------------------------------------ kernel A
-// energy-only inside/outside -> filtered base-pair masks of every sequence of the chunk
-LIN_KERNEL(8) relem_lin_filter_kernel(LinKArgs a LIN_SMEM_ARG) {
-#ifndef RELEM_HOST_EMU
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-#endif
-  const LinLayout& lay = a.lay;
-  const int blk = LIN_BLOCK_IDX;
-  if (blk >= a.count) return;
-  const int n = a.b.order[a.base + blk];
-  double* slot = a.scratch + (unsigned long long)blk * lay.stride;
-  LinCtx& c = lin_setup(a, smem_raw, n);
-  const SeqView& q = c.q;
-  unsigned* bp = (unsigned*)(smem_raw + lay.sm_bp);
-  unsigned* lf = (unsigned*)(smem_raw + lay.sm_lf);
-  unsigned* bpr = (unsigned*)(smem_raw + lay.sm_bpr);
-  unsigned* lfr = (unsigned*)(smem_raw + lay.sm_lfr);
-  double* red = (double*)(smem_raw + lay.sm_red);
-  int* ctr = (int*)(smem_raw + lay.sm_ctr);
-  const int L = q.L, W = q.W;
-  cta_canonical_mask(q, bp);
-  CTA_SYNC();
-  cta_left_mask(q, bp, lf);
-  const int total = cta_count_bits(bp, (L + 1) * lay.mw, (int*)red);
-  int nbp = total;
-  bool bad = false;
-  if (LC.en.filter) {
-    cta_right_mask(q, bp, bpr);
-    cta_right_mask(q, lf, lfr);
-    CTA_SYNC();
-    K0Tabs t0;
-    t0.P = slot + lay.kP; t0.E = slot + lay.kE; t0.M = slot + lay.kM; t0.o1 = slot + lay.k1; t0.o2 = slot + lay.k2;
-    t0.O = slot + lay.kO; t0.bP = slot + lay.kbP; t0.bE = slot + lay.kbE; t0.bM = slot + lay.kbM;
-    t0.bBl = slot + lay.kbBl; t0.bBr = slot + lay.kbBr; t0.b2 = slot + lay.kb2; t0.bO = slot + lay.kbO;
-    for (int d = 3; d <= W; ++d) lin_diagonal(L + 1 - d, d, ctr, [&](int i) { k0_inside_cell(c, t0, i, d); });
-    if (CTA_TID == 0) { ctr[0] = 0; ctr[1] = 0; }
-    if (warp_id() == 0) k0_inside_ext(c, t0);
-    CTA_SYNC();
-    const double Z0 = ld_cg(t0.O + L);
-    bad = !finite_pos(Z0);
-    if (!bad) {
-      if (warp_id() == 0) k0_outside_ext(c, t0, 1. / Z0);
-      CTA_SYNC();
-      for (int d = W; d >= 3; --d) lin_diagonal(L + 1 - d, d, ctr, [&](int i) { k0_outside_cell(c, t0, i, d); });
-      // keep pairs with ln BPP >= ln min_bpp (energy_model.hpp:257-261)
-      for (int t = CTA_TID; t < (L + 1) * lay.mw; t += CTA_NTH) {
-        int i = t / lay.mw, ww = t % lay.mw;
-        unsigned in = bp[t], outb = 0u;
-        for (int bb = 0; bb < 32; ++bb) {
-          if (!((in >> bb) & 1u)) continue;
-          int d = ww * 32 + bb;
-          double post = ld_cg(t0.P + kidx(q, i + d, d)) * ld_cg(t0.bP + kidx(q, i, d));
-          double ln = post > 0. ? log(post) : NINF;
-          if (LC.en.min_lnbpp <= ln) outb |= 1u << bb;
-        }
-        bp[t] = outb;
-      }
-      CTA_SYNC();
-      cta_left_mask(q, bp, lf);
-      nbp = cta_count_bits(bp, (L + 1) * lay.mw, (int*)red);
-    }
-  }
-  CTA_SYNC();
-  unsigned* g = (unsigned*)(slot + lay.masks);
-  const int nw = (L + 1) * lay.mw;
-  for (int t = CTA_TID; t < nw; t += CTA_NTH) { g[t] = bp[t]; g[nw + t] = lf[t]; }
-  if (CTA_TID == 0) {
-    slot[lay.hdr + 3] = bad ? 1. : 0.;
-    a.out.bpp_eff[n] = (double)nbp / (double)total;
-    if (bad) a.flag[n] = 1;
-  }
 }
 
 RDEV CTabs lin_tabs(const LinLayout& lay, double* slot) {
@@ -267,31 +170,191 @@ RDEV CTabs lin_tabs(const LinLayout& lay, double* slot) {
   t.bch = (unsigned)lay.bch; t.boch = (unsigned)lay.boch;
   return t;
 }
+RDEV K0Tabs lin_k0tabs(const LinLayout& lay, double* slot) {
+  K0Tabs t0;
+  t0.P = slot + lay.kP; t0.E = slot + lay.kE; t0.M = slot + lay.kM; t0.o1 = slot + lay.k1; t0.o2 = slot + lay.k2;
+  t0.O = slot + lay.kO; t0.bP = slot + lay.kbP; t0.bE = slot + lay.kbE; t0.bM = slot + lay.kbM;
+  t0.bBl = slot + lay.kbBl; t0.bBr = slot + lay.kbBr; t0.b2 = slot + lay.kb2; t0.bO = slot + lay.kbO;
+  return t0;
+}
 
-// ------------------------------------------------------------------------------------------------ kernel B
-// coupled inside pass + partition functions
-LIN_KERNEL(5) relem_lin_inside_kernel(LinKArgs a LIN_SMEM_ARG) {
+// ------------------------------------------------------------------------------------------------ prep
+// one CTA per sequence: bases, exp(position weights), special hairpins, canonical masks -> slot header
+LIN_KERNEL(LIN_THREADS, 8) relem_lin_prep_kernel(LinKArgs a LIN_SMEM_ARG) {
+#ifndef RELEM_HOST_EMU
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
+  LIN_SHARED int cnt_sh;
+  const LinLayout& lay = a.lay;
+  const int sk = LIN_BLOCK_IDX;
+  if (sk >= a.count) return;
+  double* slot; int n;
+  LinCtx& c = lin_attach(a, smem_raw, sk, slot, n);
+  const SeqView& q = c.q;
+  const int L = q.L;
+  const long long o = a.b.off[n];
+  unsigned char* x = (unsigned char*)(slot + lay.bytes);
+  double* wsf = slot + lay.wsf;
+  for (int t = CTA_TID; t < L; t += CTA_NTH) { x[t] = a.b.seq[o + t]; wsf[t] = exp(a.b.ws[o + t]); }
+  if (CTA_TID == 0) { x[L] = 0; x[L + 1] = 0; }
+  for (int t = CTA_TID; t < 16; t += CTA_NTH) slot[lay.hdr + t] = 0.;
+  for (int t = CTA_TID; t < lay.nch * lay.ncnt; t += CTA_NTH) slot[lay.cnt + t] = 0.;
+  CTA_SYNC();
+  cta_special_hairpins(LC.en, x, L, (signed char*)q.sp3, (signed char*)q.sp4, (signed char*)q.sp6);
+  unsigned* mk = (unsigned*)(slot + lay.masks);
+  unsigned* bp = mk; unsigned* lf = mk + lay.mask_words;
+  cta_canonical_mask(q, bp);
+  CTA_SYNC();
+  cta_left_mask(q, bp, lf);
+  const int total = cta_count_bits(bp, (L + 1) * lay.mw, &cnt_sh);
+  cta_right_mask(q, bp, mk + 2 * lay.mask_words);
+  CTA_SYNC();
+  cta_right_mask(q, lf, mk + 3 * lay.mask_words);
+  if (CTA_TID == 0) {
+    slot[lay.hdr + 4] = (double)total;
+    a.out.bpp_eff[n] = 1.;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ phases
+enum { PH_K0_IN = 0, PH_K0_OUT, PH_IN_L, PH_IN_P, PH_IN_B, PH_IN_E, PH_OUT_EM, PH_OUT_B, PH_OUT_P, PH_OUT_L };
+
+// posterior sums of the CTA -> the sequence's accumulators in its slot header
+template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot, WarpLin& w, EhAcc<NCH>& eh) {
+  const LinHMM& h = LC.h;
+  double* g = slot + lay.cnt;
+  w_sync();
+  if (!LC.p.no_prf) {
+    for (int tt = lane_id(); tt < NCH * 5 * h.n_right; tt += WARP_N) {
+      int ch = tt / (5 * h.n_right), r = tt - ch * 5 * h.n_right;
+      double v = w.cntR[tt];
+      if (v != 0.) red_add(g + ch * lay.ncnt + r, v);
+    }
+    for (int tt = lane_id(); tt < NCH * 5 * h.n_left; tt += WARP_N) {
+      int ch = tt / (5 * h.n_left), r = tt - ch * 5 * h.n_left;
+      double v = w.cntL[tt];
+      if (v != 0.) red_add(g + ch * lay.ncnt + 5 * h.n_right + r, v);
+    }
+  }
+  for (int k = 0; k < NCH * 2; ++k) {
+    double v = w_sum(eh.v[k]);
+    if (lane_id() == 0 && v != 0.) red_add(slot + lay.hdr + 8 + k, v);
+  }
+  CTA_SYNC();
+  if (!LC.p.no_prf) {
+    for (int tt = CTA_TID; tt < NCH * h.n_pair * 25; tt += CTA_NTH) {
+      int ch = tt / (h.n_pair * 25), r = tt - ch * h.n_pair * 25;
+      double v = w.pcnt[tt];
+      if (v != 0.) red_add(g + ch * lay.ncnt + 5 * (h.n_right + h.n_left) + r, v);
+    }
+  }
+}
+
+// grid = count * ntile CTAs; CTA (sk, tk) owns cells [tk*tile, (tk+1)*tile) of diagonal d of sequence slot sk,
+// its warps take them interleaved
+template <int PH, int NCH>
+LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 5)) relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
   const LinLayout& lay = a.lay;
   const int blk = LIN_BLOCK_IDX;
-  if (blk >= a.count) return;
-  const int n = a.b.order[a.base + blk];
-  double* slot = a.scratch + (unsigned long long)blk * lay.stride;
+  const int sk = blk / a.ntile, tk = blk - sk * a.ntile;
+  if (sk >= a.count) return;
+  double* slot = a.scratch + (unsigned long long)sk * lay.stride;
   if (slot[lay.hdr + 3] != 0.) return;
-  LinCtx& c = lin_setup(a, smem_raw, n);
-  lin_load_masks(a, smem_raw, c, slot);
+  int n;
+  LinCtx& c = lin_attach(a, smem_raw, sk, slot, n);
+  const SeqView& q = c.q;
+  const int d = a.d;
+  if (d > q.W) return;
+  const int ncell = q.L + 1 - d;
+  const int i0 = tk * a.tile, i1 = ncell < i0 + a.tile ? ncell : i0 + a.tile;
+  if (i0 >= ncell) return;
+  const int w0 = warp_id(), nw = n_warps();
+  if (PH == PH_K0_IN || PH == PH_K0_OUT) {
+    K0Tabs t0 = lin_k0tabs(lay, slot);
+    for (int i = i0 + w0; i < i1; i += nw) {
+      if (PH == PH_K0_IN) k0_inside_cell(c, t0, i, d);
+      else k0_outside_cell(c, t0, i, d);
+    }
+    return;
+  }
+  CTabs t = lin_tabs(lay, slot);
+  const LinHMM& h = LC.h;
+  if (PH >= PH_IN_L && PH <= PH_IN_E) {
+    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + w0 * lay.warp_bytes_in, q.S, lay.Wmax, 1, h.n_max, 0, 0, true);
+    for (int i = i0 + w0; i < i1; i += nw) {
+      if (PH == PH_IN_L) lin_in_L(c, t, i, d, w);
+      if (PH == PH_IN_P) { if (ok_P(q, i, d)) lin_in_P(c, t, i, d, w); }
+      if (PH == PH_IN_B) {
+        bool gB = ok_B(q, i, d), gM = ok_M(q, i, d);
+        if (gB || gM) lin_in_B(c, t, i, d, ok_P(q, i, d), gB, gM, w);
+      }
+      if (PH == PH_IN_E) { if (ok_E(q, i, d)) lin_in_E(c, t, i, d, ok_M(q, i, d), w); }
+    }
+    return;
+  }
+  if (PH >= PH_OUT_EM) {
+    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + w0 * lay.warp_bytes_out, q.S, lay.Wmax, NCH, h.n_max, h.n_right,
+                               h.n_left, false);
+    w.pcnt = (double*)(smem_raw + lay.sm_pcnt);
+    for (int tt = CTA_TID; tt < NCH * h.n_pair * 25; tt += CTA_NTH) w.pcnt[tt] = 0.;
+    for (int tt = lane_id(); tt < NCH * 5 * h.n_right; tt += WARP_N) w.cntR[tt] = 0.;
+    for (int tt = lane_id(); tt < NCH * 5 * h.n_left; tt += WARP_N) w.cntL[tt] = 0.;
+    CTA_SYNC();
+    EhAcc<NCH> eh;
+    for (int k = 0; k < NCH * 2; ++k) eh.v[k] = 0.;
+    for (int i = i0 + w0; i < i1; i += nw) {
+      if (PH == PH_OUT_EM) {
+        bool gE = ok_E(q, i, d), gM = ok_M(q, i, d);
+        if (gE || gM) lin_out_EM<NCH>(c, t, i, d, gE, gM, w, eh);
+      }
+      if (PH == PH_OUT_B) { if (ok_B(q, i, d)) lin_out_B<NCH>(c, t, i, d, ok_M(q, i, d), w); }
+      if (PH == PH_OUT_P) { if (ok_P(q, i, d)) lin_out_P<NCH>(c, t, i, d, ok_B(q, i, d), w, eh); }
+      if (PH == PH_OUT_L) lin_out_L<NCH>(c, t, i, d, d >= 3 && ok_E(q, i, d), w, eh);
+    }
+    lin_flush_counts<NCH>(lay, slot, w, eh);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ exterior rows
+// one warp per sequence.  WHICH: 0 energy-only inside, 1 energy-only outside, 2 coupled inside (+ partition functions,
+// root weights), 3 coupled outside
+template <int WHICH, int NCH> LIN_KERNEL(32, 16) relem_lin_ext_kernel(LinKArgs a LIN_SMEM_ARG) {
+#ifndef RELEM_HOST_EMU
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
+  const LinLayout& lay = a.lay;
+  const int sk = LIN_BLOCK_IDX;
+  if (sk >= a.count) return;
+  double* slot = a.scratch + (unsigned long long)sk * lay.stride;
+  if (slot[lay.hdr + 3] != 0.) return;
+  int n;
+  LinCtx& c = lin_attach(a, smem_raw, sk, slot, n);
   const SeqView& q = c.q;
   const LinHMM& h = LC.h;
-  const int L = q.L, W = q.W, S = q.S;
-  int* ctr = (int*)(smem_raw + lay.sm_ctr);
-  WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + warp_id() * lay.warp_bytes_in, S, lay.Wmax, 1, h.n_max, 0, 0, true);
+  const int L = q.L, S = q.S;
+  if (WHICH == 0) {
+    K0Tabs t0 = lin_k0tabs(lay, slot);
+    k0_inside_ext(c, t0);
+    w_sync();
+    const double Z0 = ld_cg(t0.O + L);
+    if (!finite_pos(Z0)) {
+      if (lane_id() == 0) { slot[lay.hdr + 3] = 1.; a.flag[n] = 1; }
+    }
+    return;
+  }
+  if (WHICH == 1) {
+    K0Tabs t0 = lin_k0tabs(lay, slot);
+    k0_outside_ext(c, t0, 1. / ld_cg(t0.O + L));
+    return;
+  }
   CTabs t = lin_tabs(lay, slot);
-  for (int d = 0; d <= W; ++d) { lin_inside_diag(c, t, d, w); CTA_SYNC(); }
-  if (warp_id() == 0) lin_inside_ext(c, t, w);
-  CTA_SYNC();
-  if (CTA_TID == 0) {
+  if (WHICH == 2) {
+    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp, S, lay.Wmax, 1, h.n_max, 0, 0, true);
+    lin_inside_ext(c, t, w);
+    w_sync();
     const double r00 = h.s00 >= 0 ? ld_cg(t.aO + (unsigned)L * S + h.s00) : 0.;
     const double rM2 = h.s0M2 >= 0 ? ld_cg(t.aO + (unsigned)L * S + h.s0M2) : 0.;
     const double rM1 = h.s0M1 >= 0 ? ld_cg(t.aO + (unsigned)L * S + h.s0M1) : 0.;
@@ -299,114 +362,134 @@ LIN_KERNEL(5) relem_lin_inside_kernel(LinKArgs a LIN_SMEM_ARG) {
     const int kind = a.b.kind[n];
     // every partition function the trainer tests must be representable; otherwise the log-space path decides
     const bool bad = !finite_pos(Ztt) || (kind != 2 && !finite_pos(Ztf)) || !(Zft >= 0. && Zft < (-NINF));
-    slot[lay.hdr + 0] = Ztt; slot[lay.hdr + 1] = Ztf; slot[lay.hdr + 2] = Zft;
-    if (bad) { slot[lay.hdr + 3] = 1.; a.flag[n] = 1; }
-    else {
+    if (bad) {
+      if (lane_id() == 0) { slot[lay.hdr + 3] = 1.; a.flag[n] = 1; }
+      return;
+    }
+    if (lane_id() == 0) {
+      slot[lay.hdr + 0] = Ztt; slot[lay.hdr + 1] = Ztf; slot[lay.hdr + 2] = Zft;
       const double shift = -(double)L * LC.p.ln_kappa;  // ln Z = ln Z^ - L ln kappa
       a.out.Z[n * 3 + 0] = log(Ztt) + shift;
       a.out.Z[n * 3 + 1] = Ztf > 0. ? log(Ztf) + shift : NINF;
       a.out.Z[n * 3 + 2] = Zft > 0. ? log(Zft) + shift : NINF;
       a.out.skipped[n] = 0;
     }
+    // root weights of the outside pass: channel 0 = Zo (all three roots), channel 1 = the restricted condition;
+    // NCH = 1 carries their difference
+    double rw[NCH][3];
+    {
+      double o0 = 1. / Ztt;
+      double x00 = 0., xM = 0.;
+      if (kind == 1) xM = 1. / Ztf;
+      else x00 = Zft > 0. ? 1. / Zft : 0.;
+      if (NCH == 2) {
+        rw[0][0] = o0; rw[0][1] = o0; rw[0][2] = o0;
+        rw[NCH - 1][0] = x00; rw[NCH - 1][1] = xM; rw[NCH - 1][2] = xM;
+      } else {
+        rw[0][0] = o0 - x00; rw[0][1] = o0 - xM; rw[0][2] = o0 - xM;
+      }
+    }
+    for (int tt = lane_id(); tt < NCH * S; tt += WARP_N) {
+      int ch = tt / S, s = tt - ch * S;
+      double v = 0.;
+      if (s == h.s00) v = rw[ch][0];
+      if (s == h.s0M2) v = rw[ch][1];
+      if (s == h.s0M1) v = rw[ch][2];
+      t.bO[ch * t.boch + (unsigned)L * S + s] = v;
+    }
+    return;
+  }
+  if (WHICH == 3) {
+    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp, S, lay.Wmax, NCH, h.n_max, h.n_right, h.n_left, false);
+    w.pcnt = (double*)(smem_raw + lay.sm_pcnt);
+    for (int tt = lane_id(); tt < NCH * h.n_pair * 25; tt += WARP_N) w.pcnt[tt] = 0.;
+    for (int tt = lane_id(); tt < NCH * 5 * h.n_right; tt += WARP_N) w.cntR[tt] = 0.;
+    for (int tt = lane_id(); tt < NCH * 5 * h.n_left; tt += WARP_N) w.cntL[tt] = 0.;
+    w_sync();
+    EhAcc<NCH> eh;
+    for (int k = 0; k < NCH * 2; ++k) eh.v[k] = 0.;
+    lin_outside_ext<NCH>(c, t, w);
+    lin_flush_counts<NCH>(lay, slot, w, eh);
   }
 }
 
-// ------------------------------------------------------------------------------------------------ kernel C
-// coupled outside pass in gather form + expected counts
-template <int NCH> LIN_KERNEL(5) relem_lin_outside_kernel(LinKArgs a LIN_SMEM_ARG) {
+// ------------------------------------------------------------------------------------------------ filter
+// one CTA per sequence: keep pairs with ln BPP >= ln min_bpp (energy_model.hpp:257-261), rebuild the four masks
+LIN_KERNEL(LIN_THREADS, 8) relem_lin_filter_kernel(LinKArgs a LIN_SMEM_ARG) {
+#ifndef RELEM_HOST_EMU
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
+  LIN_SHARED int cnt_sh;
+  const LinLayout& lay = a.lay;
+  const int sk = LIN_BLOCK_IDX;
+  if (sk >= a.count) return;
+  double* slot = a.scratch + (unsigned long long)sk * lay.stride;
+  if (slot[lay.hdr + 3] != 0.) return;
+  int n;
+  LinCtx& c = lin_attach(a, smem_raw, sk, slot, n);
+  const SeqView& q = c.q;
+  const int L = q.L;
+  K0Tabs t0 = lin_k0tabs(lay, slot);
+  unsigned* mk = (unsigned*)(slot + lay.masks);
+  unsigned* bp = mk; unsigned* lf = mk + lay.mask_words;
+  for (int t = CTA_TID; t < (L + 1) * lay.mw; t += CTA_NTH) {
+    int i = t / lay.mw, ww = t % lay.mw;
+    unsigned in = bp[t], outb = 0u;
+    for (int bb = 0; bb < 32; ++bb) {
+      if (!((in >> bb) & 1u)) continue;
+      int d = ww * 32 + bb;
+      double post = ld_cg(t0.P + kidx(q, i + d, d)) * ld_cg(t0.bP + kidx(q, i, d));
+      double ln = post > 0. ? log(post) : NINF;
+      if (LC.en.min_lnbpp <= ln) outb |= 1u << bb;
+    }
+    bp[t] = outb;
+  }
+  CTA_SYNC();
+  cta_left_mask(q, bp, lf);
+  const int nbp = cta_count_bits(bp, (L + 1) * lay.mw, &cnt_sh);
+  cta_right_mask(q, bp, mk + 2 * lay.mask_words);
+  CTA_SYNC();
+  cta_right_mask(q, lf, mk + 3 * lay.mask_words);
+  if (CTA_TID == 0) a.out.bpp_eff[n] = (double)nbp / slot[lay.hdr + 4];
+}
+
+// ------------------------------------------------------------------------------------------------ fold
+// one CTA per sequence: per-entry emission sums -> theta-shaped counts; results
+template <int NCH> LIN_KERNEL(LIN_THREADS, 8) relem_lin_fold_kernel(LinKArgs a LIN_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
   const LinLayout& lay = a.lay;
-  const int blk = LIN_BLOCK_IDX;
-  if (blk >= a.count) return;
-  const int n = a.b.order[a.base + blk];
-  double* slot = a.scratch + (unsigned long long)blk * lay.stride;
-  if (slot[lay.hdr + 3] != 0.) return;
-  LinCtx& c = lin_setup(a, smem_raw, n);
-  lin_load_masks(a, smem_raw, c, slot);
-  const SeqView& q = c.q;
   const LinHMM& h = LC.h;
-  const int L = q.L, W = q.W, S = q.S, NT = LC.p.n_theta;
-  int* ctr = (int*)(smem_raw + lay.sm_ctr);
-  double* sen = (double*)(smem_raw + lay.sm_en);
-  double* seh = (double*)(smem_raw + lay.sm_eh);
-  double* pcnt = (double*)(smem_raw + lay.sm_pcnt);
-  WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + warp_id() * lay.warp_bytes_out, S, lay.Wmax, NCH, h.n_max,
-                             h.n_right, h.n_left, false);
-  w.pcnt = pcnt;
-  CTabs t = lin_tabs(lay, slot);
-  const double Ztt = slot[lay.hdr + 0], Ztf = slot[lay.hdr + 1], Zft = slot[lay.hdr + 2];
-  const int kind = a.b.kind[n];
-  // root weights of the outside pass: channel 0 = Zo (all three roots), channel 1 = the restricted condition
-  double rw[NCH][3];
-  {
-    double o0 = 1. / Ztt;
-    double x00 = 0., xM = 0.;
-    if (kind == 1) xM = 1. / Ztf;
-    else x00 = Zft > 0. ? 1. / Zft : 0.;
-    if (NCH == 2) {
-      rw[0][0] = o0; rw[0][1] = o0; rw[0][2] = o0;
-      rw[NCH - 1][0] = x00; rw[NCH - 1][1] = xM; rw[NCH - 1][2] = xM;
-    } else {
-      rw[0][0] = o0 - x00; rw[0][1] = o0 - xM; rw[0][2] = o0 - xM;
-    }
-  }
-  for (int tt = CTA_TID; tt < NCH * S; tt += CTA_NTH) {
-    int ch = tt / S, s = tt - ch * S;
-    double v = 0.;
-    if (s == h.s00) v = rw[ch][0];
-    if (s == h.s0M2) v = rw[ch][1];
-    if (s == h.s0M1) v = rw[ch][2];
-    t.bO[ch * t.boch + (unsigned)L * S + s] = v;
-  }
+  const int NT = LC.p.n_theta;
+  const int sk = LIN_BLOCK_IDX;
+  if (sk >= a.count) return;
+  double* slot = a.scratch + (unsigned long long)sk * lay.stride;
+  if (slot[lay.hdr + 3] != 0.) return;
+  const int n = a.b.order[a.base + sk];
+  double* sen = (double*)smem_raw;  // [NCH][NT]
   for (int tt = CTA_TID; tt < NCH * NT; tt += CTA_NTH) sen[tt] = 0.;
-  for (int tt = CTA_TID; tt < NCH * h.n_pair * 25; tt += CTA_NTH) pcnt[tt] = 0.;
-  for (int tt = CTA_TID; tt < 8; tt += CTA_NTH) seh[tt] = 0.;
-  for (int tt = lane_id(); tt < NCH * 5 * h.n_right; tt += WARP_N) w.cntR[tt] = 0.;
-  for (int tt = lane_id(); tt < NCH * 5 * h.n_left; tt += WARP_N) w.cntL[tt] = 0.;
   CTA_SYNC();
-  EhAcc<NCH> eh;
-  for (int k = 0; k < NCH * 2; ++k) eh.v[k] = 0.;
-  if (warp_id() == 0) lin_outside_ext<NCH>(c, t, w);
-  CTA_SYNC();
-  for (int d = W; d >= 0; --d) { lin_outside_diag<NCH>(c, t, d, w, eh); CTA_SYNC(); }
-  // ---- fold the per-entry emission sums into theta-shaped counts
-  w_sync();
-  if (!LC.p.no_prf) {
-    for (int tt = lane_id(); tt < NCH * 5 * h.n_right; tt += WARP_N) {
-      int ch = tt / (5 * h.n_right), r = tt - ch * 5 * h.n_right;
-      int idx = ld_ro(h.r_en + r);
-      double v = w.cntR[tt];
-      if (idx >= 0 && v != 0.) sm_add(sen + ch * NT + idx, v);
-    }
-    for (int tt = lane_id(); tt < NCH * 5 * h.n_left; tt += WARP_N) {
-      int ch = tt / (5 * h.n_left), r = tt - ch * 5 * h.n_left;
-      int idx = ld_ro(h.l_en + r);
-      double v = w.cntL[tt];
-      if (idx >= 0 && v != 0.) sm_add(sen + ch * NT + idx, v);
-    }
-  }
-  for (int k = 0; k < NCH * 2; ++k) {
-    double v = w_sum(eh.v[k]);
-    if (lane_id() == 0 && v != 0.) sm_add(seh + k, v);
-  }
-  CTA_SYNC();
-  if (!LC.p.no_prf) {
-    for (int tt = CTA_TID; tt < NCH * h.n_pair * 25; tt += CTA_NTH) {
-      int ch = tt / (h.n_pair * 25), r = tt - ch * h.n_pair * 25;
-      double v = pcnt[tt];
-      if (v == 0.) continue;
-      int i1 = ld_ro(h.p_en1 + r), i2 = ld_ro(h.p_en2 + r);
+  const double* g = slot + lay.cnt;
+  const int nR = 5 * h.n_right, nL = 5 * h.n_left;
+  for (int tt = CTA_TID; tt < NCH * lay.ncnt; tt += CTA_NTH) {
+    int ch = tt / lay.ncnt, r = tt - ch * lay.ncnt;
+    double v = ld_cg(g + tt);
+    if (v == 0.) continue;
+    if (r < nR) { int idx = ld_ro(h.r_en + r); if (idx >= 0) sm_add(sen + ch * NT + idx, v); }
+    else if (r < nR + nL) { int idx = ld_ro(h.l_en + (r - nR)); if (idx >= 0) sm_add(sen + ch * NT + idx, v); }
+    else {
+      int i1 = ld_ro(h.p_en1 + (r - nR - nL)), i2 = ld_ro(h.p_en2 + (r - nR - nL));
       if (i1 >= 0) sm_add(sen + ch * NT + i1, v);
       if (i2 >= 0) sm_add(sen + ch * NT + i2, v);
     }
   }
   CTA_SYNC();
-  // ---- results; non-finite counts mean the scaled tables overflowed somewhere: let the log-space path redo it
+  // non-finite counts mean the scaled tables overflowed somewhere: let the log-space path redo the sequence
   bool okv = true;
   for (int tt = 0; tt < NCH * NT; ++tt) okv = okv && (sen[tt] - sen[tt] == 0.);
-  for (int k = 0; k < NCH * 2; ++k) okv = okv && (seh[k] - seh[k] == 0.);
+  double ehv[NCH * 2];
+  for (int k = 0; k < NCH * 2; ++k) { ehv[k] = ld_cg(slot + lay.hdr + 8 + k); okv = okv && (ehv[k] - ehv[k] == 0.); }
   if (!okv) {
     if (CTA_TID == 0) a.flag[n] = 1;
     return;
@@ -416,9 +499,9 @@ template <int NCH> LIN_KERNEL(5) relem_lin_outside_kernel(LinKArgs a LIN_SMEM_AR
     a.out.ENx[(long long)n * NT + tt] = NCH == 2 ? sen[(NCH - 1) * NT + tt] : 0.;
   }
   if (CTA_TID == 0) {
-    a.out.EH[n * 4 + 0] = seh[0]; a.out.EH[n * 4 + 1] = seh[1];
-    a.out.EH[n * 4 + 2] = NCH == 2 ? seh[(NCH - 1) * 2] : 0.;
-    a.out.EH[n * 4 + 3] = NCH == 2 ? seh[(NCH - 1) * 2 + 1] : 0.;
+    a.out.EH[n * 4 + 0] = ehv[0]; a.out.EH[n * 4 + 1] = ehv[1];
+    a.out.EH[n * 4 + 2] = NCH == 2 ? ehv[(NCH - 1) * 2] : 0.;
+    a.out.EH[n * 4 + 3] = NCH == 2 ? ehv[(NCH - 1) * 2 + 1] : 0.;
   }
 }
 
@@ -426,68 +509,136 @@ template <int NCH> LIN_KERNEL(5) relem_lin_outside_kernel(LinKArgs a LIN_SMEM_AR
 struct LinState {
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  void* k0pow = nullptr;
+  size_t k0pow_n = 0;
 };
 
 LinState* lin_state_create() { return new LinState(); }
 void lin_state_destroy(LinState* s) {
   if (!s) return;
 #ifdef RELEM_HOST_EMU
-  std::free(s->scratch);
+  std::free(s->scratch); std::free(s->k0pow);
 #else
   if (s->scratch) cudaFree(s->scratch);
+  if (s->k0pow) cudaFree(s->k0pow);
 #endif
   delete s;
+}
+
+namespace {
+struct Runner {
+  LinKArgs a;
+  int smem_in, smem_out, smem_small, smem_ext_in, smem_ext_out;
+  int launches = 0;
+#ifdef RELEM_HOST_EMU
+  std::vector<unsigned char> smem;
+#else
+  cudaStream_t stream;
+#endif
+};
+}  // namespace
+
+#ifdef RELEM_HOST_EMU
+#define LIN_LAUNCH(R, KERN, GRID, THREADS, SMEM) \
+  do { for (int b__ = 0; b__ < (GRID); ++b__) KERN((R).a, (R).smem.data(), b__); ++(R).launches; } while (0)
+#else
+#define LIN_LAUNCH(R, KERN, GRID, THREADS, SMEM)                                                              \
+  do {                                                                                                        \
+    if ((SMEM) > 48 * 1024)                                                                                   \
+      cudaFuncSetAttribute((const void*)KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (SMEM));           \
+    KERN<<<(GRID), (THREADS), (SMEM), (R).stream>>>((R).a);                                                   \
+    ++(R).launches;                                                                                           \
+  } while (0)
+#endif
+
+template <int PH, int NCH> static void launch_phase(Runner& r, int d, int tile, int smem) {
+  const int ncell_max = r.a.lay.Lmax + 1 - d;
+  if (ncell_max <= 0) return;
+  if (tile > ncell_max) tile = ncell_max;
+  r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile;
+  LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, NCH>), r.a.count * r.a.ntile, LIN_THREADS, smem);
+}
+
+template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
+  const int W = r.a.lay.Wmax, cnt = r.a.count;
+  const int WIDE = 1 << 20;  // one CTA per sequence and diagonal (phases that touch few cells)
+  LIN_LAUNCH(r, relem_lin_prep_kernel, cnt, LIN_THREADS, r.smem_small);
+  if (filter) {
+    for (int d = 3; d <= W; ++d) launch_phase<PH_K0_IN, 1>(r, d, 32, r.smem_small);
+    LIN_LAUNCH(r, (relem_lin_ext_kernel<0, 1>), cnt, 32, r.smem_small);
+    LIN_LAUNCH(r, (relem_lin_ext_kernel<1, 1>), cnt, 32, r.smem_small);
+    for (int d = W; d >= 3; --d) launch_phase<PH_K0_OUT, 1>(r, d, 32, r.smem_small);
+    LIN_LAUNCH(r, relem_lin_filter_kernel, cnt, LIN_THREADS, r.smem_small);
+  }
+  for (int d = 0; d <= W; ++d) {
+    launch_phase<PH_IN_L, 1>(r, d, 32, r.smem_in);
+    if (d >= 5) {
+      launch_phase<PH_IN_P, 1>(r, d, WIDE, r.smem_in);
+      launch_phase<PH_IN_B, 1>(r, d, 32, r.smem_in);
+    }
+    if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, WIDE, r.smem_in);
+  }
+  LIN_LAUNCH(r, (relem_lin_ext_kernel<2, NCH>), cnt, 32, r.smem_ext_in);
+  LIN_LAUNCH(r, (relem_lin_ext_kernel<3, NCH>), cnt, 32, r.smem_ext_out);
+  for (int d = W; d >= 0; --d) {
+    if (d >= 3) launch_phase<PH_OUT_EM, NCH>(r, d, 64, r.smem_out);
+    if (d >= 5) {
+      launch_phase<PH_OUT_B, NCH>(r, d, 32, r.smem_out);
+      launch_phase<PH_OUT_P, NCH>(r, d, WIDE, r.smem_out);
+    }
+    launch_phase<PH_OUT_L, NCH>(r, d, 32, r.smem_out);
+  }
+  LIN_LAUNCH(r, (relem_lin_fold_kernel<NCH>), cnt, LIN_THREADS, NCH * NT * 8 + 16);
 }
 
 int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* launches, std::string& err) {
   if (kernel_ms) *kernel_ms = 0.f;
   if (launches) *launches = 0;
-  const int nwarps = LIN_THREADS / 32;
   LinConst hc;
   hc.h = in.h; hc.p = in.p; hc.en = in.en; hc.el = in.el; hc.k0 = in.kappa0; hc.k0sq = in.kappa0 * in.kappa0;
-  LinKArgs a;
+  Runner r;
+  LinKArgs& a = r.a;
   a.b = in.b; a.out = in.out; a.flag = in.flag;
   const int nseq = in.b.nseq;
+  a.lay = make_lin_layout(std::max(1, in.Lmax), in.max_span, in.h, in.nch);
+  const LinLayout& lay = a.lay;
+  r.smem_small = lay.sm_warp;
+  r.smem_in = lay.sm_warp + LIN_WARPS * lay.warp_bytes_in;
+  r.smem_out = lay.sm_warp + LIN_WARPS * lay.warp_bytes_out;
+  r.smem_ext_in = lay.sm_warp + lay.warp_bytes_in;
+  r.smem_ext_out = lay.sm_warp + lay.warp_bytes_out;
+  const int NT = in.p.n_theta;
+  std::vector<double> kp(lay.Wmax + 3);
+  for (int t = 0; t < (int)kp.size(); ++t) kp[t] = std::pow(in.kappa0, (double)t);
+  size_t per = (size_t)lay.stride * sizeof(double);
 #ifdef RELEM_HOST_EMU
   LC = hc;
-  a.lay = make_lin_layout(std::max(1, in.Lmax), in.max_span, in.h, in.p.n_theta, in.nch, 1);
-  size_t need = (size_t)a.lay.stride * sizeof(double);
-  if (need > st->scratch_bytes) {
+  if (per > st->scratch_bytes) {
     std::free(st->scratch);
-    st->scratch = std::malloc(need);
-    st->scratch_bytes = st->scratch ? need : 0;
+    st->scratch = std::malloc(per);
+    st->scratch_bytes = st->scratch ? per : 0;
   }
   if (!st->scratch) { err = "scratch allocation failed"; return 3; }
-  a.scratch = (double*)st->scratch;
-  std::vector<unsigned char> smem(std::max(a.lay.sm_total_in, a.lay.sm_total_out) + 64);
+  std::free(st->k0pow);
+  st->k0pow = std::malloc(kp.size() * 8);
+  std::memcpy(st->k0pow, kp.data(), kp.size() * 8);
+  a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow;
+  r.smem.assign(std::max(std::max(r.smem_out, r.smem_in), NT * in.nch * 8 + 16) + 64, 0);
   for (int k = 0; k < nseq; ++k) {
     // poison: the gather passes must never read an entry they did not write
-    { double* p = (double*)st->scratch; for (size_t z = 0; z < need / 8; ++z) p[z] = std::nan(""); }
+    { double* p = (double*)st->scratch; for (size_t z = 0; z < per / 8; ++z) p[z] = std::nan(""); }
     a.base = k; a.count = 1;
-    relem_lin_filter_kernel(a, smem.data(), 0);
-    relem_lin_inside_kernel(a, smem.data(), 0);
-    if (in.nch == 2) relem_lin_outside_kernel<2>(a, smem.data(), 0);
-    else relem_lin_outside_kernel<1>(a, smem.data(), 0);
+    if (in.nch == 2) run_chunk<2>(r, in.en.filter != 0, NT);
+    else run_chunk<1>(r, in.en.filter != 0, NT);
   }
-  if (launches) *launches = 3 * nseq;
-  (void)nwarps;
+  if (launches) *launches = r.launches;
   return 0;
 #else
-  a.lay = make_lin_layout(std::max(1, in.Lmax), in.max_span, in.h, in.p.n_theta, in.nch, nwarps);
-  if (a.lay.sm_total_out > 227 * 1024) { err = "sequence too long for the linear-space kernel's shared memory"; return 1; }
-  const void* kout = in.nch == 2 ? (const void*)relem_lin_outside_kernel<2> : (const void*)relem_lin_outside_kernel<1>;
-  cudaError_t e;
-  if ((e = cudaFuncSetAttribute((const void*)relem_lin_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.lay.sm_total_k0)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute((const void*)relem_lin_inside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.lay.sm_total_in)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(kout, cudaFuncAttributeMaxDynamicSharedMemorySize, a.lay.sm_total_out)) != cudaSuccess) {
-    err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
-    return 2;
-  }
+  if (r.smem_out > 227 * 1024) { err = "pattern too large for the linear-space kernel's shared memory"; return 1; }
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  size_t per = (size_t)a.lay.stride * sizeof(double);
   long long by_mem = (long long)(((double)(free_b + st->scratch_bytes) * 0.70) / (double)per);
-  long long nslots = std::min<long long>(std::min<long long>(nseq, (long long)in.sm_count * 32), by_mem);
+  long long nslots = std::min<long long>(nseq, by_mem);
   if (in.max_slots > 0) nslots = std::min<long long>(nslots, in.max_slots);
   if (nslots < 1) { err = "not enough device memory for one sequence slot"; return 3; }
   size_t need = (size_t)nslots * per;
@@ -497,24 +648,28 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
     if (cudaMalloc(&st->scratch, need) != cudaSuccess) { err = "scratch allocation failed"; return 3; }
     st->scratch_bytes = need;
   }
-  cudaStream_t stream = (cudaStream_t)in.stream;
-  e = cudaMemcpyToSymbolAsync(LC, &hc, sizeof(LinConst), 0, cudaMemcpyHostToDevice, stream);
+  if (st->k0pow_n < kp.size()) {
+    if (st->k0pow) cudaFree(st->k0pow);
+    st->k0pow = nullptr; st->k0pow_n = 0;
+    if (cudaMalloc(&st->k0pow, kp.size() * 8) != cudaSuccess) { err = "allocation failed"; return 3; }
+    st->k0pow_n = kp.size();
+  }
+  r.stream = (cudaStream_t)in.stream;
+  cudaError_t e = cudaMemcpyAsync(st->k0pow, kp.data(), kp.size() * 8, cudaMemcpyHostToDevice, r.stream);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(LC, &hc, sizeof(LinConst), 0, cudaMemcpyHostToDevice, r.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(r.stream);  // kp / hc are stack objects
   if (e != cudaSuccess) { err = std::string("constant upload: ") + cudaGetErrorString(e); return 2; }
-  a.scratch = (double*)st->scratch;
+  a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  cudaEventRecord(e0, stream);
-  int nl = 0;
+  cudaEventRecord(e0, r.stream);
   for (int base = 0; base < nseq; base += (int)nslots) {
     a.base = base; a.count = std::min<int>((int)nslots, nseq - base);
-    relem_lin_filter_kernel<<<a.count, LIN_THREADS, a.lay.sm_total_k0, stream>>>(a);
-    relem_lin_inside_kernel<<<a.count, LIN_THREADS, a.lay.sm_total_in, stream>>>(a);
-    if (in.nch == 2) relem_lin_outside_kernel<2><<<a.count, LIN_THREADS, a.lay.sm_total_out, stream>>>(a);
-    else relem_lin_outside_kernel<1><<<a.count, LIN_THREADS, a.lay.sm_total_out, stream>>>(a);
-    nl += 3;
+    if (in.nch == 2) run_chunk<2>(r, in.en.filter != 0, NT);
+    else run_chunk<1>(r, in.en.filter != 0, NT);
   }
   e = cudaGetLastError();
-  cudaEventRecord(e1, stream);
+  cudaEventRecord(e1, r.stream);
   if (e != cudaSuccess) { err = std::string("linear-space kernel launch: ") + cudaGetErrorString(e); return 2; }
   e = cudaEventSynchronize(e1);
   if (e != cudaSuccess) { err = std::string("linear-space kernels: ") + cudaGetErrorString(e); return 2; }
@@ -522,7 +677,7 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (kernel_ms) *kernel_ms = ms;
-  if (launches) *launches = nl;
+  if (launches) *launches = r.launches;
   return 0;
 #endif
 }
