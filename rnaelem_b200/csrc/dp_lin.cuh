@@ -172,9 +172,43 @@ LIN_NOINLINE F2 boltz2(double tsc) {
 struct K0Tabs {
   double *P, *E, *M, *o1, *o2, *O;
   double *bP, *bE, *bM, *bBl, *bBr, *b2, *bO;
+  double* Pm;        // P(k,l) times the interior mismatch factor on the inner pair's side (by right end, like P)
+  double* bEm;       // outside E(i,j) times the interior mismatch factor on the closing pair's side
+  const double* G;   // [32][32] internal[u1+u2] * ninio[|u1-u2|] * kappa0^(u1+u2) for u1,u2 >= 3
 };
 
-RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
+// Interior loops of the energy-only pass.  For u1,u2 >= 3 the loop energy is separable (energy_param.hpp:781-794:
+// length term + asymmetry term + one mismatch term per closing pair, always from the generic mismatch table), so the
+// sum over inner pairs is  mm(outer) * sum_{k,l} [P(k,l) mm(inner)] * G[u1][u2]  with the bracket stored once per
+// pair: two loads and one FMA per candidate.  The remaining ("special": stack, bulges, 1x1, 1x2, 2x2, 1xn, 2x3) candidates
+// are compacted across the warp and evaluated by the full case analysis, one per lane.
+// sbuf: per-warp scratch of 128 ints.
+RDEV void k0_specials_push(int* sbuf, int& ns, unsigned sp, int u1) {
+  // exclusive prefix of the per-lane counts, then every lane writes its own candidates
+  int cnt = w_popc(sp), pre = cnt;
+#ifndef RELEM_HOST_EMU
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xFFFFFFFFu, pre, o);
+    if ((int)(threadIdx.x & 31) >= o) pre += v;
+  }
+  int tot = __shfl_sync(0xFFFFFFFFu, pre, 31);
+  pre -= cnt;
+#else
+  int tot = cnt;
+  pre = 0;
+#endif
+  int pos = ns + pre;
+  while (sp) {
+    int b = w_ffs(sp) - 1;
+    sp &= sp - 1;
+    if (pos < 128) sbuf[pos] = (u1 << 8) | b;
+    ++pos;
+  }
+  ns += tot;
+}
+
+
+RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* sbuf) {
   const SeqView& q = c.q;
   const DevEnergy& el = LC.el;
   const int j = i + d, lane = lane_id();
@@ -212,7 +246,7 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
   if (gE) {
     const int C = c.Ceff;
     const int lo = d - C > 0 ? d - C : 0;
-    double acc = 0.;
+    double acc = 0., accg = 0.;
     for (int u10 = 0; u10 <= C; u10 += WARP_N) {
       int u1 = u10 + lane, k = i + u1;
       unsigned m = 0u;
@@ -220,19 +254,47 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
         m = win_bits(q.bp + k * q.mw, q.mw, lo, d - u1 - lo + 1);
         if (u1 == 0) m &= ~(1u << (d - lo));
       }
-      while (m) {
-        int b = w_ffs(m) - 1;
-        m &= m - 1;
-        int dd = lo + b, l = k + dd, u2 = d - u1 - dd;
-        acc += t.P[kidx(q, l, dd)] * c.k0pow[u1 + u2] * (ne ? 1. : nl_l_loop(&q, i - 1, j, k, l - 1));
+      // generic candidates: u1 >= 3 and u2 = d-u1-dd >= 3  <=>  bit index b = dd-lo <= d-u1-3-lo
+      unsigned gen = 0u;
+      if (!ne && u1 >= 3) {
+        int top = d - u1 - 3 - lo;
+        if (top >= 0) gen = m & (top >= 31 ? 0xFFFFFFFFu : ((2u << top) - 1u));
       }
+      unsigned sp = m & ~gen;
+      while (gen) {
+        int b = w_ffs(gen) - 1;
+        gen &= gen - 1;
+        int dd = lo + b, l = k + dd, u2 = d - u1 - dd;
+        accg += t.Pm[kidx(q, l, dd)] * ld_ro(t.G + u1 * 32 + u2);
+      }
+      int ns = 0;
+      k0_specials_push(sbuf, ns, sp, u1);
+      w_sync();
+      if (ns > 128) ns = 128;  // cannot happen: at most 3*31 + 28*3 specials
+      for (int z = lane; z < ns; z += WARP_N) {
+        int e = sbuf[z], su1 = e >> 8, b = e & 255;
+        int sk = i + su1, dd = lo + b, l = sk + dd, u2 = d - su1 - dd;
+        acc += t.P[kidx(q, l, dd)] * c.k0pow[su1 + u2] * (ne ? 1. : nl_l_loop(&q, i - 1, j, sk, l - 1));
+      }
+      w_sync();
     }
+    if (!ne) {
+      int type = bp_type(q.x[i - 1], q.x[j]);
+      accg *= ld_ro(el.mismatch_i + (type * 5 + q.x[i]) * 5 + q.x[j - 1]);
+    }
+    acc += accg;
     vE = w_sum(acc);
     if (gM) vE += vM * (ne ? 1. : nl_l_ext(&q, j, i - 1, 0) * (el.mlclosing * el.mlintern));
     if (d >= 1) vE += c.k0pow[d] * (ne ? 1. : nl_l_hairpin(&q, i - 1, j));
   }
   if (lane == 0) {
-    if (gP) t.P[kidx(q, j, d)] = vP;
+    if (gP) {
+      t.P[kidx(q, j, d)] = vP;
+      // inner-pair side mismatch of a generic interior loop: pair (i, j-1), neighbours x[j] and x[i-1]
+      double mmf = 0.;
+      if (i >= 1 && j < q.L) mmf = ld_ro(el.mismatch_i + (bp_type(q.x[j - 1], q.x[i]) * 5 + q.x[j]) * 5 + q.x[i - 1]);
+      t.Pm[kidx(q, j, d)] = vP * mmf;
+    }
     if (gB) { t.o1[kidx(q, i, d)] = v1; t.o2[kidx(q, j, d)] = v2; }
     if (gM) t.M[kidx(q, i, d)] = vM;
     if (gE) t.E[kidx(q, i, d)] = vE;
@@ -283,7 +345,7 @@ RDEV void k0_outside_ext(const LinCtx& c, const K0Tabs& t, double rootw) {
   }
 }
 
-RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
+RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* sbuf) {
   const SeqView& q = c.q;
   const DevEnergy& el = LC.el;
   const int j = i + d, lane = lane_id(), L = q.L, W = q.W;
@@ -330,7 +392,7 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
     // enclosing pairs: this cell is the inner pair (k=i,l=j) of E(i',j')
     const int C = c.Ceff;
     const int hi = W < d + C + 2 ? W : d + C + 2;
-    double acc = 0.;
+    double acc = 0., accg = 0.;
     for (int u10 = 0; u10 <= C; u10 += WARP_N) {
       int u1 = u10 + lane, i2 = i - u1, lo = d + u1 + 2;
       unsigned m = 0u;
@@ -338,18 +400,37 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d) {
         m = win_bits(q.bp + (i2 - 1) * q.mw, q.mw, lo, hi - lo + 1);
         if (u1 == 0) m &= ~1u;
       }
-      while (m) {
-        int u2 = w_ffs(m) - 1;
-        m &= m - 1;
-        int j2 = j + u2;
-        acc += t.bE[kidx(q, i2, d + u1 + u2)] * c.k0pow[u1 + u2] * (ne ? 1. : nl_l_loop(&q, i2 - 1, j2, i, j - 1));
+      unsigned gen = (!ne && u1 >= 3) ? (m & ~7u) : 0u;   // bit index = u2
+      unsigned sp = m & ~gen;
+      while (gen) {
+        int u2 = w_ffs(gen) - 1;
+        gen &= gen - 1;
+        accg += t.bEm[kidx(q, i2, d + u1 + u2)] * ld_ro(t.G + u1 * 32 + u2);
       }
+      int ns = 0;
+      k0_specials_push(sbuf, ns, sp, u1);
+      w_sync();
+      if (ns > 128) ns = 128;
+      for (int z = lane; z < ns; z += WARP_N) {
+        int e = sbuf[z], su1 = e >> 8, u2 = e & 255;
+        int si2 = i - su1, j2 = j + u2;
+        acc += t.bE[kidx(q, si2, d + su1 + u2)] * c.k0pow[su1 + u2] * (ne ? 1. : nl_l_loop(&q, si2 - 1, j2, i, j - 1));
+      }
+      w_sync();
     }
+    if (!ne && i >= 1 && j < L)
+      accg *= ld_ro(el.mismatch_i + (bp_type(q.x[j - 1], q.x[i]) * 5 + q.x[j]) * 5 + q.x[i - 1]);
+    else accg = 0.;
+    acc += accg;
     bP += w_sum(acc);
   }
   if (lane == 0) {
     if (gP) t.bP[kidx(q, i, d)] = bP;
-    if (gE) t.bE[kidx(q, i, d)] = bE;
+    if (gE) {
+      t.bE[kidx(q, i, d)] = bE;
+      // closing-pair side mismatch of a generic interior loop: pair (i-1, j), neighbours x[i] and x[j-1]
+      t.bEm[kidx(q, i, d)] = bE * ld_ro(el.mismatch_i + (bp_type(q.x[i - 1], q.x[j]) * 5 + q.x[i]) * 5 + q.x[j - 1]);
+    }
     if (gM) t.bM[kidx(q, i, d)] = bM;
     if (gB) { t.bBl[kidx(q, i, d)] = bB; t.bBr[kidx(q, j, d)] = bB; t.b2[kidx(q, i, d)] = b2; }
   }
@@ -1038,14 +1119,25 @@ template <int NCH> RDEV void lin_out_B(const LinCtx& c, const CTabs& t, int i, i
     for (int pz = lane; pz < h.n_split; pz += WARP_N) {
       int a = ld_ro(h.spL_ord + pz);
       int s = ld_ro(h.sp_tgt + a), sr = ld_ro(h.sp_r + a);
-      double v[NCH];
-      for (int ch = 0; ch < NCH; ++ch) v[ch] = 0.;
-      for (int tt = 0; tt < nk; ++tt) {
-        int d2 = w.kbuf[tt];
-        double sib = t.a2[sib0 + d2 * sstep + sr];
-        for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBl[ch * t.bch + rb + (unsigned)d2 * S + s] * sib;
+      double v[NCH], v2[NCH];
+      for (int ch = 0; ch < NCH; ++ch) { v[ch] = 0.; v2[ch] = 0.; }
+      const double* ps = t.a2 + sib0 + sr;
+      const double* pb = t.bBl + rb + s;
+      int tt = 0;
+      for (; tt + 1 < nk; tt += 2) {   // two split points in flight
+        int da = w.kbuf[tt], db = w.kbuf[tt + 1];
+        double sa = ps[da * sstep], sb = ps[db * sstep];
+        for (int ch = 0; ch < NCH; ++ch) {
+          v[ch] += pb[ch * t.bch + (unsigned)da * S] * sa;
+          v2[ch] += pb[ch * t.bch + (unsigned)db * S] * sb;
+        }
       }
-      for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+      if (tt < nk) {
+        int da = w.kbuf[tt];
+        double sa = ps[da * sstep];
+        for (int ch = 0; ch < NCH; ++ch) v[ch] += pb[ch * t.bch + (unsigned)da * S] * sa;
+      }
+      for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch] + v2[ch];
     }
     w_sync();
     for (int s = lane; s < S; s += WARP_N)
@@ -1076,14 +1168,25 @@ template <int NCH> RDEV void lin_out_B(const LinCtx& c, const CTabs& t, int i, i
     for (int pz = lane; pz < h.n_split; pz += WARP_N) {
       int a = ld_ro(h.spR_ord + pz);
       int s = ld_ro(h.sp_tgt + a), sl = ld_ro(h.sp_l + a);
-      double v[NCH];
-      for (int ch = 0; ch < NCH; ++ch) v[ch] = 0.;
-      for (int tt = 0; tt < nk; ++tt) {
-        int d2 = w.kbuf[tt];
-        double sib = t.a1[sib0 - d2 * sstep + sl];
-        for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bBr[ch * t.bch + rb + (unsigned)d2 * S + s] * sib;
+      double v[NCH], v2[NCH];
+      for (int ch = 0; ch < NCH; ++ch) { v[ch] = 0.; v2[ch] = 0.; }
+      const double* ps = t.a1 + sib0 + sl;
+      const double* pb = t.bBr + rb + s;
+      int tt = 0;
+      for (; tt + 1 < nk; tt += 2) {
+        int da = w.kbuf[tt], db = w.kbuf[tt + 1];
+        double sa = ps[-da * sstep], sb = ps[-db * sstep];
+        for (int ch = 0; ch < NCH; ++ch) {
+          v[ch] += pb[ch * t.bch + (unsigned)da * S] * sa;
+          v2[ch] += pb[ch * t.bch + (unsigned)db * S] * sb;
+        }
       }
-      for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
+      if (tt < nk) {
+        int da = w.kbuf[tt];
+        double sa = ps[-da * sstep];
+        for (int ch = 0; ch < NCH; ++ch) v[ch] += pb[ch * t.bch + (unsigned)da * S] * sa;
+      }
+      for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch] + v2[ch];
     }
     w_sync();
     for (int s = lane; s < S; s += WARP_N)

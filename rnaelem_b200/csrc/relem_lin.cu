@@ -42,7 +42,7 @@ struct LinLayout {
   unsigned long long stride;  // doubles per slot
   unsigned long long aP, aE, aM, a1, a2, aLl, aLr, aO;
   unsigned long long bP, bEl, bEr, bM, bBl, bBr, b2, bL, bO, bch, boch;
-  unsigned long long kP, kE, kM, k1, k2, kO, kbP, kbE, kbM, kbBl, kbBr, kb2, kbO;
+  unsigned long long kP, kE, kM, k1, k2, kO, kbP, kbE, kbM, kbBl, kbBr, kb2, kbO, kPm, kbEm;
   // per-slot header
   unsigned long long hdr;    // [16]: Z^tt, Z^tf, Z^ft, bad, canonical pair count, -, -, -, EH[nch*2]
   unsigned long long wsf;    // [Lmax+1] exp(position weight)
@@ -74,6 +74,7 @@ static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int nc
   lay.kO = take(Lmax + 1);
   lay.kbP = take(cells); lay.kbE = take(cells); lay.kbM = take(cells); lay.kbBl = take(cells); lay.kbBr = take(cells);
   lay.kb2 = take(cells); lay.kbO = take(Lmax + 1);
+  lay.kPm = take(cells); lay.kbEm = take(cells);
   lay.hdr = take(16);
   lay.wsf = take(Lmax + 1);
   lay.cnt = take((unsigned long long)nch * lay.ncnt);
@@ -99,6 +100,7 @@ struct LinKArgs {
   LinLayout lay;
   double* scratch;
   const double* k0pow;
+  int kp_n;          // entries of k0pow before the G table
   EstepOut out;
   unsigned char* flag;
 };
@@ -170,12 +172,28 @@ RDEV CTabs lin_tabs(const LinLayout& lay, double* slot) {
   t.bch = (unsigned)lay.bch; t.boch = (unsigned)lay.boch;
   return t;
 }
-RDEV K0Tabs lin_k0tabs(const LinLayout& lay, double* slot) {
+RDEV K0Tabs lin_k0tabs(const LinLayout& lay, double* slot, const double* G) {
   K0Tabs t0;
+  t0.Pm = slot + lay.kPm; t0.bEm = slot + lay.kbEm; t0.G = G;
   t0.P = slot + lay.kP; t0.E = slot + lay.kE; t0.M = slot + lay.kM; t0.o1 = slot + lay.k1; t0.o2 = slot + lay.k2;
   t0.O = slot + lay.kO; t0.bP = slot + lay.kbP; t0.bE = slot + lay.kbE; t0.bM = slot + lay.kbM;
   t0.bBl = slot + lay.kbBl; t0.bBr = slot + lay.kbBr; t0.b2 = slot + lay.kb2; t0.bO = slot + lay.kbO;
   return t0;
+}
+
+// separable part of the generic interior-loop weight (see K0Tabs::G)
+LIN_KERNEL(LIN_THREADS, 8) relem_lin_gtab_kernel(LinKArgs a LIN_SMEM_ARG) {
+#ifdef RELEM_HOST_EMU
+  (void)smem_raw; (void)emu_block;
+#endif
+  double* G = const_cast<double*>(a.k0pow) + a.kp_n;
+  for (int t = CTA_TID; t < 1024; t += CTA_NTH) {
+    int u1 = t >> 5, u2 = t & 31, du = u1 > u2 ? u1 - u2 : u2 - u1;
+    double v = 0.;
+    if (u1 >= 3 && u2 >= 3 && u1 + u2 <= 30)
+      v = ld_ro(LC.el.internal + u1 + u2) * ld_ro(LC.el.ninio + du) * a.k0pow[u1 + u2];
+    G[t] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ prep
@@ -273,10 +291,11 @@ LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 5)) relem_lin_phase_kernel(LinKAr
   if (i0 >= ncell) return;
   const int w0 = warp_id(), nw = n_warps();
   if (PH == PH_K0_IN || PH == PH_K0_OUT) {
-    K0Tabs t0 = lin_k0tabs(lay, slot);
+    K0Tabs t0 = lin_k0tabs(lay, slot, a.k0pow + a.kp_n);
     for (int i = i0 + w0; i < i1; i += nw) {
-      if (PH == PH_K0_IN) k0_inside_cell(c, t0, i, d);
-      else k0_outside_cell(c, t0, i, d);
+      int* sbuf = (int*)(smem_raw + lay.sm_warp) + w0 * 128;
+      if (PH == PH_K0_IN) k0_inside_cell(c, t0, i, d, sbuf);
+      else k0_outside_cell(c, t0, i, d, sbuf);
     }
     return;
   }
@@ -336,7 +355,7 @@ template <int WHICH, int NCH> LIN_KERNEL(32, 16) relem_lin_ext_kernel(LinKArgs a
   const LinHMM& h = LC.h;
   const int L = q.L, S = q.S;
   if (WHICH == 0) {
-    K0Tabs t0 = lin_k0tabs(lay, slot);
+    K0Tabs t0 = lin_k0tabs(lay, slot, a.k0pow + a.kp_n);
     k0_inside_ext(c, t0);
     w_sync();
     const double Z0 = ld_cg(t0.O + L);
@@ -346,7 +365,7 @@ template <int WHICH, int NCH> LIN_KERNEL(32, 16) relem_lin_ext_kernel(LinKArgs a
     return;
   }
   if (WHICH == 1) {
-    K0Tabs t0 = lin_k0tabs(lay, slot);
+    K0Tabs t0 = lin_k0tabs(lay, slot, a.k0pow + a.kp_n);
     k0_outside_ext(c, t0, 1. / ld_cg(t0.O + L));
     return;
   }
@@ -429,7 +448,7 @@ LIN_KERNEL(LIN_THREADS, 8) relem_lin_filter_kernel(LinKArgs a LIN_SMEM_ARG) {
   LinCtx& c = lin_attach(a, smem_raw, sk, slot, n);
   const SeqView& q = c.q;
   const int L = q.L;
-  K0Tabs t0 = lin_k0tabs(lay, slot);
+  K0Tabs t0 = lin_k0tabs(lay, slot, a.k0pow + a.kp_n);
   unsigned* mk = (unsigned*)(slot + lay.masks);
   unsigned* bp = mk; unsigned* lf = mk + lay.mask_words;
   for (int t = CTA_TID; t < (L + 1) * lay.mw; t += CTA_NTH) {
@@ -528,7 +547,7 @@ void lin_state_destroy(LinState* s) {
 namespace {
 struct Runner {
   LinKArgs a;
-  int smem_in, smem_out, smem_small, smem_ext_in, smem_ext_out;
+  int smem_in, smem_out, smem_small, smem_k0, smem_ext_in, smem_ext_out;
   int launches = 0;
 #ifdef RELEM_HOST_EMU
   std::vector<unsigned char> smem;
@@ -561,22 +580,21 @@ template <int PH, int NCH> static void launch_phase(Runner& r, int d, int tile, 
 
 template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
   const int W = r.a.lay.Wmax, cnt = r.a.count;
-  const int WIDE = 1 << 20;  // one CTA per sequence and diagonal (phases that touch few cells)
   LIN_LAUNCH(r, relem_lin_prep_kernel, cnt, LIN_THREADS, r.smem_small);
   if (filter) {
-    for (int d = 3; d <= W; ++d) launch_phase<PH_K0_IN, 1>(r, d, 32, r.smem_small);
+    for (int d = 3; d <= W; ++d) launch_phase<PH_K0_IN, 1>(r, d, 32, r.smem_k0);
     LIN_LAUNCH(r, (relem_lin_ext_kernel<0, 1>), cnt, 32, r.smem_small);
     LIN_LAUNCH(r, (relem_lin_ext_kernel<1, 1>), cnt, 32, r.smem_small);
-    for (int d = W; d >= 3; --d) launch_phase<PH_K0_OUT, 1>(r, d, 32, r.smem_small);
+    for (int d = W; d >= 3; --d) launch_phase<PH_K0_OUT, 1>(r, d, 32, r.smem_k0);
     LIN_LAUNCH(r, relem_lin_filter_kernel, cnt, LIN_THREADS, r.smem_small);
   }
   for (int d = 0; d <= W; ++d) {
     launch_phase<PH_IN_L, 1>(r, d, 32, r.smem_in);
     if (d >= 5) {
-      launch_phase<PH_IN_P, 1>(r, d, WIDE, r.smem_in);
+      launch_phase<PH_IN_P, 1>(r, d, 64, r.smem_in);
       launch_phase<PH_IN_B, 1>(r, d, 32, r.smem_in);
     }
-    if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, WIDE, r.smem_in);
+    if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, 128, r.smem_in);
   }
   LIN_LAUNCH(r, (relem_lin_ext_kernel<2, NCH>), cnt, 32, r.smem_ext_in);
   LIN_LAUNCH(r, (relem_lin_ext_kernel<3, NCH>), cnt, 32, r.smem_ext_out);
@@ -584,7 +602,7 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
     if (d >= 3) launch_phase<PH_OUT_EM, NCH>(r, d, 64, r.smem_out);
     if (d >= 5) {
       launch_phase<PH_OUT_B, NCH>(r, d, 32, r.smem_out);
-      launch_phase<PH_OUT_P, NCH>(r, d, WIDE, r.smem_out);
+      launch_phase<PH_OUT_P, NCH>(r, d, 128, r.smem_out);
     }
     launch_phase<PH_OUT_L, NCH>(r, d, 32, r.smem_out);
   }
@@ -603,13 +621,16 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   a.lay = make_lin_layout(std::max(1, in.Lmax), in.max_span, in.h, in.nch);
   const LinLayout& lay = a.lay;
   r.smem_small = lay.sm_warp;
+  r.smem_k0 = lay.sm_warp + LIN_WARPS * 128 * 4;
   r.smem_in = lay.sm_warp + LIN_WARPS * lay.warp_bytes_in;
   r.smem_out = lay.sm_warp + LIN_WARPS * lay.warp_bytes_out;
   r.smem_ext_in = lay.sm_warp + lay.warp_bytes_in;
   r.smem_ext_out = lay.sm_warp + lay.warp_bytes_out;
   const int NT = in.p.n_theta;
-  std::vector<double> kp(lay.Wmax + 3);
-  for (int t = 0; t < (int)kp.size(); ++t) kp[t] = std::pow(in.kappa0, (double)t);
+  // kappa0 powers [0, KP) followed by the separable interior-loop table G[32][32]; the device fills G (gtab kernel)
+  const int KP = std::max(256, (lay.Wmax + 3 + 31) & ~31);
+  std::vector<double> kp(KP + 1024, 0.);
+  for (int t = 0; t < KP; ++t) kp[t] = std::pow(in.kappa0, (double)t);
   size_t per = (size_t)lay.stride * sizeof(double);
 #ifdef RELEM_HOST_EMU
   LC = hc;
@@ -622,8 +643,9 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   std::free(st->k0pow);
   st->k0pow = std::malloc(kp.size() * 8);
   std::memcpy(st->k0pow, kp.data(), kp.size() * 8);
-  a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow;
+  a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
   r.smem.assign(std::max(std::max(r.smem_out, r.smem_in), NT * in.nch * 8 + 16) + 64, 0);
+  LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
   for (int k = 0; k < nseq; ++k) {
     // poison: the gather passes must never read an entry they did not write
     { double* p = (double*)st->scratch; for (size_t z = 0; z < per / 8; ++z) p[z] = std::nan(""); }
@@ -659,10 +681,11 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(LC, &hc, sizeof(LinConst), 0, cudaMemcpyHostToDevice, r.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(r.stream);  // kp / hc are stack objects
   if (e != cudaSuccess) { err = std::string("constant upload: ") + cudaGetErrorString(e); return 2; }
-  a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow;
+  a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, r.stream);
+  LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
   for (int base = 0; base < nseq; base += (int)nslots) {
     a.base = base; a.count = std::min<int>((int)nslots, nseq - base);
     if (in.nch == 2) run_chunk<2>(r, in.en.filter != 0, NT);
