@@ -11,7 +11,10 @@ N > 1 the NCCL all-reduce of those P+3 doubles.
 metric  dp_cells_per_s = band cells x 3 coupled passes (inside + 2 outside, the reference's pass count) per second,
         whole job.  `value`: batch resident in HBM.  `e2e`: the host-buffer entry point relem_estep (H2D of the
         batch from pinned memory and D2H of the result inside the timed region).
-roofline  dominant kernel relem_estep_lin_kernel against HBM: algorithmic bytes = cells x 168 x S.
+roofline  the E-step is one wavefront of small kernels (relem_lin_phase_kernel<phase> per span and phase, 486 launches
+        per chunk of sequences); `achieved` = algorithmic bytes (cells x 168 x S) / summed device time of
+        those launches (CUDA events on the launch stream) against the measured HBM copy bandwidth; `traffic` = measured
+        DRAM bytes of the same launches (ncu dram__bytes_read+write, profiles/r1_dram_traffic.json) scaled to the batch.
 cpu_baseline / --impl reference  the unmodified reference binary (oracle/_ref/RNAelem train ... --max-iter 1) on
         all host cores, on a bounded sample of the same workload.
 """
@@ -281,6 +284,10 @@ def main_own(args):
         else:
             peak, which = 6650.0, "fallback"
         achieved = step_bytes / (kms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+        if os.path.exists(tpath):
+            traffic = int(json.load(open(tpath))["dram_bytes_per_sequence_evaluation"] * 2 * npos)
         line = {"metric": "dp_cells_per_s", "value": value, "unit": "dp_cells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -290,8 +297,9 @@ def main_own(args):
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": which,
-                             "kernel_ms": kms, "algorithmic_bytes_per_launch": int(step_bytes)},
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": which,
+                             "kernel_ms": kms, "algorithmic_bytes_per_launch": int(step_bytes),
+                             "note": "one 'launch' = the whole wavefront of phase kernels over the step's batch"},
                 "phase_share": phases}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

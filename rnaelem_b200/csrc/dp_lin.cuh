@@ -596,9 +596,7 @@ template <class F> RDEV void walk_left_flank(const LinCtx& c, int i, int d, Warp
       batch_push(c, w, n, ok, l, j2, tsc);
     }
   }
-  w_sync();
-  if (n) flush(n);
-  w_sync();
+  if (n) { w_sync(); flush(n); w_sync(); }
 }
 // cell (l,j) as the right unpaired flank L(l,j) of E(i',j) with inner pair (k,l); pushes (k, i')
 template <class F> RDEV void walk_right_flank(const LinCtx& c, int l, int d, WarpLin& w, F flush) {
@@ -627,9 +625,7 @@ template <class F> RDEV void walk_right_flank(const LinCtx& c, int l, int d, War
       batch_push(c, w, n, ok, k, i2, tsc);
     }
   }
-  w_sync();
-  if (n) flush(n);
-  w_sync();
+  if (n) { w_sync(); flush(n); w_sync(); }
 }
 
 // ------------------------------------------------------------------------------------------------- inside
@@ -1418,13 +1414,15 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
   }
   if (d >= 1 && d <= c.Ceff && h.n_quad > 0) {
     if (i >= 1) {
-      for (int a = lane; a < h.n_quad; a += WARP_N)
-        for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
-      w_sync();
       const unsigned eb = cidx(q, i, 0);
       bool any = false;
       walk_left_flank(c, i, d, w, [&](int n) {
-        any = true;
+        if (!any) {   // most cells flank no interior loop at all: set the accumulators up only when one shows up
+          for (int a = lane; a < h.n_quad; a += WARP_N)
+            for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
+          w_sync();
+          any = true;
+        }
         for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
           int a = ld_ro(h.qL_ord + pz);
           int s = ld_ro(h.q_tgt + a), s1 = ld_ro(h.q_s1 + a), s3 = ld_ro(h.q_s3 + a);
@@ -1445,13 +1443,15 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
       w_sync();
     }
     if (j + 1 <= L) {
-      for (int a = lane; a < h.n_quad; a += WARP_N)
-        for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
-      w_sync();
       const unsigned eb = cidx(q, j, 0);
       bool any = false;
       walk_right_flank(c, i, d, w, [&](int n) {
-        any = true;
+        if (!any) {
+          for (int a = lane; a < h.n_quad; a += WARP_N)
+            for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
+          w_sync();
+          any = true;
+        }
         for (int pz = lane; pz < h.n_quad; pz += WARP_N) {
           int a = ld_ro(h.qR_ord + pz);
           int s = ld_ro(h.q_tgt + a), s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a);
