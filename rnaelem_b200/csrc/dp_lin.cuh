@@ -492,22 +492,44 @@ RDEV double seg_sum(const double* part, const int* off, int s) {
 }
 
 // all lanes call; lanes with ok append (ia, ib, tsc) and the two Boltzmann factors exp(lambda_slot * tsc)
-RDEV void batch_push(const LinCtx& c, WarpLin& w, int& n, bool ok, int ia, int ib, double tsc) {
+// Structural candidates are collected in two stages: the mask scans only append (ia, ib) ids (ballot compaction);
+// once a batch is complete its energies are evaluated with ONE candidate per lane, so the ~300-instruction case
+// analysis + two exponentials run at full lane occupancy however sparse the scan was.  Candidates with a forbidden
+// energy stay in the batch with weight 0.
+RDEV void batch_add(WarpLin& w, int& n, bool ok, int ia, int ib) {
   unsigned bal = w_ballot(ok);
   if (ok) {
     int pos = n + w_popc(bal & lanemask_lt());
-    w.bi[pos] = ia; w.bj[pos] = ib; w.bt[pos] = tsc;
-    F2 ff = boltz2(tsc);
-    w.bf0[pos] = ff.f0;
-    w.bf1[pos] = ff.f1;
+    w.bi[pos] = ia; w.bj[pos] = ib;
   }
   n += w_popc(bal);
 }
-#define LIN_ROOM(n, flush)                            \
+// energy(ia, ib) -> tsc (log-Boltzmann weight of the structural transition)
+template <class E> RDEV void batch_eval(WarpLin& w, int n, E energy) {
+  w_sync();
+  const bool ne = LC.en.no_ene != 0;
+  for (int z = lane_id(); z < n; z += WARP_N) {
+    double tsc = 0., f0 = 1., f1 = 1.;
+    if (!ne) {
+      tsc = energy(w.bi[z], w.bj[z]);
+      if (tsc > NINF) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
+      else { tsc = 0.; f0 = 0.; f1 = 0.; }
+    }
+    w.bt[z] = tsc; w.bf0[z] = f0; w.bf1[z] = f1;
+  }
+  w_sync();
+}
+#define LIN_ROOM(n, energy, flush)                    \
   if ((n) > LIN_CAP - WARP_N) {                       \
-    w_sync();                                         \
+    batch_eval(w, n, energy);                         \
     flush(n);                                         \
     (n) = 0;                                          \
+    w_sync();                                         \
+  }
+#define LIN_DONE(n, energy, flush)                    \
+  if (n) {                                            \
+    batch_eval(w, n, energy);                         \
+    flush(n);                                         \
     w_sync();                                         \
   }
 
@@ -516,6 +538,7 @@ template <class F> RDEV void walk_inner(const LinCtx& c, int i, int d, WarpLin& 
   const SeqView& q = c.q;
   const int j = i + d, C = c.Ceff, lane = lane_id();
   const int lo = d - C > 0 ? d - C : 0;
+  auto energy = [&](int k, int l) { return nl_e_loop(&q, i - 1, j, k, l - 1); };
   int n = 0;
   for (int u10 = 0; u10 <= C; u10 += WARP_N) {
     int u1 = u10 + lane, k = i + u1;
@@ -525,26 +548,21 @@ template <class F> RDEV void walk_inner(const LinCtx& c, int i, int d, WarpLin& 
       if (u1 == 0) m &= ~(1u << (d - lo));
     }
     while (w_any(m != 0u)) {
-      LIN_ROOM(n, flush)
+      LIN_ROOM(n, energy, flush)
       bool has = m != 0u;
       int b = 0;
       if (has) { b = w_ffs(m) - 1; m &= m - 1; }
-      int l = k + lo + b;
-      double tsc = 0.;
-      bool ok = has;
-      if (has && !LC.en.no_ene) { tsc = nl_e_loop(&q, i - 1, j, k, l - 1); ok = tsc > NINF; }
-      batch_push(c, w, n, ok, k, l, tsc);
+      batch_add(w, n, has, k, k + lo + b);
     }
   }
-  w_sync();
-  if (n) flush(n);
-  w_sync();
+  LIN_DONE(n, energy, flush)
 }
 // enclosing pairs: E(i',j') that have (k=i,l=j) as inner pair
 template <class F> RDEV void walk_outer(const LinCtx& c, int i, int d, WarpLin& w, F flush) {
   const SeqView& q = c.q;
   const int j = i + d, C = c.Ceff, lane = lane_id(), W = q.W;
   const int hi = W < d + C + 2 ? W : d + C + 2;
+  auto energy = [&](int i2, int j2) { return nl_e_loop(&q, i2 - 1, j2, i, j - 1); };
   int n = 0;
   for (int u10 = 0; u10 <= C; u10 += WARP_N) {
     int u1 = u10 + lane, i2 = i - u1, lo = d + u1 + 2;
@@ -554,20 +572,14 @@ template <class F> RDEV void walk_outer(const LinCtx& c, int i, int d, WarpLin& 
       if (u1 == 0) m &= ~1u;
     }
     while (w_any(m != 0u)) {
-      LIN_ROOM(n, flush)
+      LIN_ROOM(n, energy, flush)
       bool has = m != 0u;
       int u2 = 0;
       if (has) { u2 = w_ffs(m) - 1; m &= m - 1; }
-      int j2 = j + u2;
-      double tsc = 0.;
-      bool ok = has;
-      if (has && !LC.en.no_ene) { tsc = nl_e_loop(&q, i2 - 1, j2, i, j - 1); ok = tsc > NINF; }
-      batch_push(c, w, n, ok, i2, j2, tsc);
+      batch_add(w, n, has, i2, j + u2);
     }
   }
-  w_sync();
-  if (n) flush(n);
-  w_sync();
+  LIN_DONE(n, energy, flush)
 }
 // cell (i,k) as the left unpaired flank L(i,k) of E(i,j') with inner pair (k,l); pushes (l, j')
 template <class F> RDEV void walk_left_flank(const LinCtx& c, int i, int d, WarpLin& w, F flush) {
@@ -575,6 +587,7 @@ template <class F> RDEV void walk_left_flank(const LinCtx& c, int i, int d, Warp
   const int k = i + d, C = c.Ceff, lane = lane_id(), W = q.W;
   const unsigned* rk = q.bp + k * q.mw;
   const unsigned* ri = q.bp + (i - 1) * q.mw;
+  auto energy = [&](int l, int j2) { return nl_e_loop(&q, i - 1, j2, k, l - 1); };
   int n = 0;
   for (int dd0 = 0; dd0 <= W; dd0 += WARP_N) {
     int dd = dd0 + lane, l = k + dd;
@@ -585,18 +598,14 @@ template <class F> RDEV void walk_left_flank(const LinCtx& c, int i, int d, Warp
       if (hi >= lo) m = win_bits(ri, q.mw, lo, hi - lo + 1);
     }
     while (w_any(m != 0u)) {
-      LIN_ROOM(n, flush)
+      LIN_ROOM(n, energy, flush)
       bool has = m != 0u;
       int u2 = 0;
       if (has) { u2 = w_ffs(m) - 1; m &= m - 1; }
-      int j2 = l + u2;
-      double tsc = 0.;
-      bool ok = has;
-      if (has && !LC.en.no_ene) { tsc = nl_e_loop(&q, i - 1, j2, k, l - 1); ok = tsc > NINF; }
-      batch_push(c, w, n, ok, l, j2, tsc);
+      batch_add(w, n, has, l, l + u2);
     }
   }
-  if (n) { w_sync(); flush(n); w_sync(); }
+  LIN_DONE(n, energy, flush)
 }
 // cell (l,j) as the right unpaired flank L(l,j) of E(i',j) with inner pair (k,l); pushes (k, i')
 template <class F> RDEV void walk_right_flank(const LinCtx& c, int l, int d, WarpLin& w, F flush) {
@@ -604,6 +613,7 @@ template <class F> RDEV void walk_right_flank(const LinCtx& c, int l, int d, War
   const int j = l + d, C = c.Ceff, lane = lane_id(), W = q.W;
   const unsigned* rl = c.bpr + l * q.mw;
   const unsigned* rj = c.bpr + (j + 1) * q.mw;
+  auto energy = [&](int k, int i2) { return nl_e_loop(&q, i2 - 1, j, k, l - 1); };
   int n = 0;
   for (int dd0 = 0; dd0 <= W; dd0 += WARP_N) {
     int dd = dd0 + lane, k = l - dd;
@@ -614,18 +624,14 @@ template <class F> RDEV void walk_right_flank(const LinCtx& c, int l, int d, War
       if (hi >= lo) m = win_bits(rj, q.mw, lo, hi - lo + 1);
     }
     while (w_any(m != 0u)) {
-      LIN_ROOM(n, flush)
+      LIN_ROOM(n, energy, flush)
       bool has = m != 0u;
       int u1 = 0;
       if (has) { u1 = w_ffs(m) - 1; m &= m - 1; }
-      int i2 = k - u1;
-      double tsc = 0.;
-      bool ok = has;
-      if (has && !LC.en.no_ene) { tsc = nl_e_loop(&q, i2 - 1, j, k, l - 1); ok = tsc > NINF; }
-      batch_push(c, w, n, ok, k, i2, tsc);
+      batch_add(w, n, has, k, k - u1);
     }
   }
-  if (n) { w_sync(); flush(n); w_sync(); }
+  LIN_DONE(n, energy, flush)
 }
 
 // ------------------------------------------------------------------------------------------------- inside
@@ -899,17 +905,13 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
     {
       const unsigned* rj = c.bpr + j * q.mw;
       int dmax = q.W < j ? q.W : j, n = 0;
+      auto energy = [&](int i, int) { return nl_e_ext(&q, i, j - 1, 1); };
       for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
-        LIN_ROOM(n, flush)
+        LIN_ROOM(n, energy, flush)
         int u = u0 + lane;
-        bool ok = u <= dmax && row_bit(rj, u);
-        double tsc = 0.;
-        if (ok && !ne) { tsc = nl_e_ext(&q, j - u, j - 1, 1); ok = tsc > NINF; }
-        batch_push(c, w, n, ok, j - u, j, tsc);
+        batch_add(w, n, u <= dmax && row_bit(rj, u), j - u, j);
       }
-      w_sync();
-      if (n) flush(n);
-      w_sync();
+      LIN_DONE(n, energy, flush)
     }
     for (int s = lane; s < S; s += WARP_N) cur[s] = seg_sum(part, h.sp_off, s);
     w_sync();
@@ -965,17 +967,13 @@ template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, Wa
     {
       const unsigned* ri = q.bp + i * q.mw;
       int dmax = q.W < L - i ? q.W : L - i, n = 0;
+      auto energy = [&](int j, int) { return nl_e_ext(&q, i, j - 1, 1); };
       for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
-        LIN_ROOM(n, flush)
+        LIN_ROOM(n, energy, flush)
         int u = u0 + lane;
-        bool ok = u <= dmax && row_bit(ri, u);
-        double tsc = 0.;
-        if (ok && !ne) { tsc = nl_e_ext(&q, i, i + u - 1, 1); ok = tsc > NINF; }
-        batch_push(c, w, n, ok, i + u, i, tsc);
+        batch_add(w, n, u <= dmax && row_bit(ri, u), i + u, i);
       }
-      w_sync();
-      if (n) flush(n);
-      w_sync();
+      LIN_DONE(n, energy, flush)
     }
     for (int s = lane; s < S; s += WARP_N)
       for (int ch = 0; ch < NCH; ++ch) w.curB[ch * S + s] = seg_sum(w.partA + ch * NM, h.spL_off, s);
