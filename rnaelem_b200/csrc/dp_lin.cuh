@@ -453,7 +453,8 @@ struct WarpLin {
   int* kbuf;      // [W+2] compacted split points
   double* cntR;   // [NCH][n_right*5] emission posterior sums per (entry, base), private to the warp
   double* cntL;   // [NCH][n_left*5]
-  double* pcnt;   // [NCH][n_pair*25] CTA-shared (atomics)
+  double* pcnt;   // pair-emission posterior sums [n_pair*25] of channel 0 in the slot header (global, RED)
+  unsigned pstride;  // channel stride of pcnt
   int n_max;
 };
 // inside = true: only what the inside pass needs (no outside staging, no counts)
@@ -486,8 +487,13 @@ RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n
 }
 
 RDEV double seg_sum(const double* part, const int* off, int s) {
+  // segments are short (mostly 0..3 entries): straight-line code for the first three, a loop for the rest
+  const int a = ld_ro(off + s), n = ld_ro(off + s + 1) - a;
   double v = 0.;
-  for (int a = ld_ro(off + s), e = ld_ro(off + s + 1); a < e; ++a) v += part[a];
+  if (n > 0) v = part[a];
+  if (n > 1) v += part[a + 1];
+  if (n > 2) v += part[a + 2];
+  for (int k = 3; k < n; ++k) v += part[a + k];
   return v;
 }
 
@@ -1027,7 +1033,7 @@ RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, boo
         double contrib = t.bP[ch * t.bch + pb + s] * wt;
         w.partA[ch * NM + pz] = contrib;
         double post = contrib * ac;
-        if (!p.no_prf && post != 0.) sm_add(w.pcnt + (ch * h.n_pair + a) * 25 + xl * 5 + xr, post);
+        if (!p.no_prf && post != 0.) red_add(w.pcnt + ch * w.pstride + a * 25 + xl * 5 + xr, post);
       }
     }
     w_sync();
@@ -1274,7 +1280,7 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
           w.partA[ch * NM + pz] = contrib;
           double post = contrib * ac;
           eh.add(ch, sl, tsc * post);
-          if (!p.no_prf && post != 0.) sm_add(w.pcnt + (ch * h.n_pair + a) * 25 + xl * 5 + xr, post);
+          if (!p.no_prf && post != 0.) red_add(w.pcnt + ch * w.pstride + a * 25 + xl * 5 + xr, post);
         }
       }
       w_sync();

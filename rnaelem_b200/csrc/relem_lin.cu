@@ -85,7 +85,7 @@ static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int nc
   auto sm = [&](int bytes) { int r = b; b += (bytes + 15) & ~15; return r; };
   lay.sm_ctx = sm((int)sizeof(LinCtx));
   lay.sm_misc = sm(64);
-  lay.sm_pcnt = sm(nch * h.n_pair * 25 * 8 + 8);
+  lay.sm_pcnt = b;
   lay.sm_warp = b;
   lay.warp_bytes_in = warp_lin_bytes(h.S, Wmax, 1, h.n_max, 0, 0, true);
   lay.warp_bytes_out = warp_lin_bytes(h.S, Wmax, nch, h.n_max, h.n_right, h.n_left, false);
@@ -243,28 +243,21 @@ template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot
   double* g = slot + lay.cnt;
   w_sync();
   if (!LC.p.no_prf) {
-    for (int tt = lane_id(); tt < NCH * 5 * h.n_right; tt += WARP_N) {
-      int ch = tt / (5 * h.n_right), r = tt - ch * 5 * h.n_right;
-      double v = w.cntR[tt];
-      if (v != 0.) red_add(g + ch * lay.ncnt + r, v);
-    }
-    for (int tt = lane_id(); tt < NCH * 5 * h.n_left; tt += WARP_N) {
-      int ch = tt / (5 * h.n_left), r = tt - ch * 5 * h.n_left;
-      double v = w.cntL[tt];
-      if (v != 0.) red_add(g + ch * lay.ncnt + 5 * h.n_right + r, v);
+    const int nR = 5 * h.n_right, nL = 5 * h.n_left;
+    for (int ch = 0; ch < NCH; ++ch) {
+      for (int r = lane_id(); r < nR; r += WARP_N) {
+        double v = w.cntR[ch * nR + r];
+        if (v != 0.) red_add(g + ch * lay.ncnt + r, v);
+      }
+      for (int r = lane_id(); r < nL; r += WARP_N) {
+        double v = w.cntL[ch * nL + r];
+        if (v != 0.) red_add(g + ch * lay.ncnt + nR + r, v);
+      }
     }
   }
   for (int k = 0; k < NCH * 2; ++k) {
     double v = w_sum(eh.v[k]);
     if (lane_id() == 0 && v != 0.) red_add(slot + lay.hdr + 8 + k, v);
-  }
-  CTA_SYNC();
-  if (!LC.p.no_prf) {
-    for (int tt = CTA_TID; tt < NCH * h.n_pair * 25; tt += CTA_NTH) {
-      int ch = tt / (h.n_pair * 25), r = tt - ch * h.n_pair * 25;
-      double v = w.pcnt[tt];
-      if (v != 0.) red_add(g + ch * lay.ncnt + 5 * (h.n_right + h.n_left) + r, v);
-    }
   }
 }
 
@@ -317,11 +310,11 @@ LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 5)) relem_lin_phase_kernel(LinKAr
   if (PH >= PH_OUT_EM) {
     WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + w0 * lay.warp_bytes_out, q.S, lay.Wmax, NCH, h.n_max, h.n_right,
                                h.n_left, false);
-    w.pcnt = (double*)(smem_raw + lay.sm_pcnt);
-    for (int tt = CTA_TID; tt < NCH * h.n_pair * 25; tt += CTA_NTH) w.pcnt[tt] = 0.;
+    w.pcnt = slot + lay.cnt + 5 * (h.n_right + h.n_left);
+    w.pstride = (unsigned)lay.ncnt;
     for (int tt = lane_id(); tt < NCH * 5 * h.n_right; tt += WARP_N) w.cntR[tt] = 0.;
     for (int tt = lane_id(); tt < NCH * 5 * h.n_left; tt += WARP_N) w.cntL[tt] = 0.;
-    CTA_SYNC();
+    w_sync();
     EhAcc<NCH> eh;
     for (int k = 0; k < NCH * 2; ++k) eh.v[k] = 0.;
     for (int i = i0 + w0; i < i1; i += nw) {
@@ -420,8 +413,8 @@ template <int WHICH, int NCH> LIN_KERNEL(32, 16) relem_lin_ext_kernel(LinKArgs a
   }
   if (WHICH == 3) {
     WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp, S, lay.Wmax, NCH, h.n_max, h.n_right, h.n_left, false);
-    w.pcnt = (double*)(smem_raw + lay.sm_pcnt);
-    for (int tt = lane_id(); tt < NCH * h.n_pair * 25; tt += WARP_N) w.pcnt[tt] = 0.;
+    w.pcnt = slot + lay.cnt + 5 * (h.n_right + h.n_left);
+    w.pstride = (unsigned)lay.ncnt;
     for (int tt = lane_id(); tt < NCH * 5 * h.n_right; tt += WARP_N) w.cntR[tt] = 0.;
     for (int tt = lane_id(); tt < NCH * 5 * h.n_left; tt += WARP_N) w.cntL[tt] = 0.;
     w_sync();
