@@ -629,17 +629,22 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
 #endif
     float ms = 0.f; int nl = 0; std::string lerr;
     int lrc = lin::lin_estep_launch(c->lin, ll, &ms, &nl, lerr);
-    if (lrc) return fail(c, lrc == 3 ? RELEM_ENOMEM : RELEM_ECUDA, "linear-space E-step: " + lerr);
-    c->timing.push_back(TimingEntry{"relem_estep_lin_kernel", ms, nl});
-    std::vector<unsigned char> flags(nseq);
-    if (!Dev::d2h(flags.data(), c->d_flag.p, nseq)) return fail(c, RELEM_ECUDA, "flag copy failed");
-    std::vector<int> redo;
-    for (int k = 0; k < nseq; ++k) if (flags[k]) redo.push_back(k);
-    n_fallback = (int)redo.size();
-    if (n_fallback) {
-      if (!upload(c->d_order2, redo)) return fail(c, RELEM_ENOMEM, "fallback list upload failed");
-      bv.order = c->d_order2.as<int>();
-      bv.nseq = n_fallback;
+    if (lrc == 1) {
+      // the automaton's lists do not fit the linear-space kernels' shared memory: whole batch on the log-space path
+      use_lin = false;
+    } else {
+      if (lrc) return fail(c, lrc == 3 ? RELEM_ENOMEM : RELEM_ECUDA, "linear-space E-step: " + lerr);
+      c->timing.push_back(TimingEntry{"relem_estep_lin_kernel", ms, nl});
+      std::vector<unsigned char> flags(nseq);
+      if (!Dev::d2h(flags.data(), c->d_flag.p, nseq)) return fail(c, RELEM_ECUDA, "flag copy failed");
+      std::vector<int> redo;
+      for (int k = 0; k < nseq; ++k) if (flags[k]) redo.push_back(k);
+      n_fallback = (int)redo.size();
+      if (n_fallback) {
+        if (!upload(c->d_order2, redo)) return fail(c, RELEM_ENOMEM, "fallback list upload failed");
+        bv.order = c->d_order2.as<int>();
+        bv.nseq = n_fallback;
+      }
     }
   }
   if (n_fallback > 0) {
