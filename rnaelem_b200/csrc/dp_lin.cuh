@@ -651,7 +651,7 @@ template <class F> RDEV void walk_right_flank(const LinCtx& c, int l, int d, War
 RDEV void lin_in_L(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int S = q.S, j = i + d, lane = lane_id();
   const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
   if (d == 0) {
@@ -688,7 +688,7 @@ RDEV void lin_in_L(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
 RDEV void lin_in_P(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int S = q.S, j = i + d, lane = lane_id();
   double* part = w.partA;
   const bool ne = LC.en.no_ene != 0;
@@ -698,7 +698,7 @@ RDEV void lin_in_P(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
   bool cPP = cP;
   double f0 = 1., f1 = 1.;
   if (cP && !ne) {
-    double tsc = nl_e_loop(&q, i, j - 1, i + 1, j - 2);
+    double tsc = nl_e_loop(&c.q, i, j - 1, i + 1, j - 2);
     cPP = tsc > NINF;
     if (cPP) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
   }
@@ -726,7 +726,7 @@ RDEV void lin_in_P(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
 RDEV void lin_in_B(const LinCtx& c, const CTabs& t, int i, int d, bool gP, bool gB, bool gM, WarpLin& w) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int S = q.S, j = i + d, lane = lane_id();
   double* cur = w.curA;   // [0..S) B of this cell
   double* part = w.partA;
@@ -779,7 +779,7 @@ RDEV void lin_in_B(const LinCtx& c, const CTabs& t, int i, int d, bool gP, bool 
     bool c2P = gP;
     double f0 = 1., f1 = 1.;
     if (gP && !ne) {
-      double tsc = nl_e_ext(&q, i, j - 1, 0) + LC.en.mlintern;
+      double tsc = nl_e_ext(&c.q, i, j - 1, 0) + LC.en.mlintern;
       c2P = tsc > NINF;
       if (c2P) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
     }
@@ -818,7 +818,7 @@ RDEV void lin_in_B(const LinCtx& c, const CTabs& t, int i, int d, bool gP, bool 
 // ---- phase E: E(i,j,s) <- M(i,j,s) | L(i,j,s) hairpin | P(k,l,s1) L(i,k,s2) L(l,j,s3)   (cells enclosed by a pair)
 RDEV void lin_in_E(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpLin& w) {
   const LinHMM& h = LC.h;
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int S = q.S, j = i + d, lane = lane_id();
   double* part = w.partA;
   const bool ne = LC.en.no_ene != 0;
@@ -846,11 +846,11 @@ RDEV void lin_in_E(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpL
   double m0 = 1., m1 = 1., h0 = 1., h1 = 1.;
   if (!ne) {
     if (gM) {
-      double tM = nl_e_ext(&q, j, i - 1, 0) + (LC.en.mlclosing + LC.en.mlintern);
+      double tM = nl_e_ext(&c.q, j, i - 1, 0) + (LC.en.mlclosing + LC.en.mlintern);
       cM = tM > NINF;
       if (cM) { F2 ff = boltz2(tM); m0 = ff.f0; m1 = ff.f1; }
     }
-    double tH = nl_e_hairpin(&q, i - 1, j);
+    double tH = nl_e_hairpin(&c.q, i - 1, j);
     cH = tH > NINF;
     if (cH) { F2 ff = boltz2(tH); h0 = ff.f0; h1 = ff.f1; }
   }
@@ -866,7 +866,7 @@ RDEV void lin_in_E(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpL
 
 // one diagonal of the inside pass: the warp's cells (static interleaved assignment), phase by phase
 RDEV void lin_inside_diag(const LinCtx& c, const CTabs& t, int d, WarpLin& w) {
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int ncell = q.L + 1 - d, w0 = warp_id(), nw = n_warps();
   for (int i = w0; i < ncell; i += nw) lin_in_L(c, t, i, d, w);
   if (d >= q.min_pair) {
@@ -886,7 +886,7 @@ RDEV void lin_inside_diag(const LinCtx& c, const CTabs& t, int d, WarpLin& w) {
 RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int S = q.S, L = q.L, lane = lane_id();
   const bool ne = LC.en.no_ene != 0;
   double* part = w.partA;
@@ -911,7 +911,7 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
     {
       const unsigned* rj = c.bpr + j * q.mw;
       int dmax = q.W < j ? q.W : j, n = 0;
-      auto energy = [&](int i, int) { return nl_e_ext(&q, i, j - 1, 1); };
+      auto energy = [&](int i, int) { return nl_e_ext(&c.q, i, j - 1, 1); };
       for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
         LIN_ROOM(n, energy, flush)
         int u = u0 + lane;
@@ -948,7 +948,7 @@ template <int NCH> struct EhAcc {
 template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int S = q.S, L = q.L, lane = lane_id(), NM = w.n_max;
   const bool ne = LC.en.no_ene != 0;
   for (int i = L - 1; i >= 0; --i) {
@@ -973,7 +973,7 @@ template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, Wa
     {
       const unsigned* ri = q.bp + i * q.mw;
       int dmax = q.W < L - i ? q.W : L - i, n = 0;
-      auto energy = [&](int j, int) { return nl_e_ext(&q, i, j - 1, 1); };
+      auto energy = [&](int j, int) { return nl_e_ext(&c.q, i, j - 1, 1); };
       for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
         LIN_ROOM(n, energy, flush)
         int u = u0 + lane;
@@ -1013,7 +1013,7 @@ template <int NCH>
 RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, bool gM, WarpLin& w, EhAcc<NCH>& eh) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int S = q.S, j = i + d, lane = lane_id(), NM = w.n_max;
   const bool ne = LC.en.no_ene != 0;
   const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
@@ -1050,7 +1050,7 @@ RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, boo
     bool cM = gE;
     double tM = 0., m0 = 1., m1 = 1.;
     if (gE && !ne) {
-      tM = nl_e_ext(&q, j, i - 1, 0) + (LC.en.mlclosing + LC.en.mlintern);
+      tM = nl_e_ext(&c.q, j, i - 1, 0) + (LC.en.mlclosing + LC.en.mlintern);
       cM = tM > NINF;
       if (cM) { F2 ff = boltz2(tM); m0 = ff.f0; m1 = ff.f1; }
     }
@@ -1096,7 +1096,7 @@ RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, boo
 template <int NCH> RDEV void lin_out_B(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpLin& w) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int S = q.S, j = i + d, lane = lane_id(), L = q.L, W = q.W, NM = w.n_max;
   const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
   double* c1 = w.curB;  // [NCH][S] 1 of this cell
@@ -1226,7 +1226,7 @@ template <int NCH>
 RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, WarpLin& w, EhAcc<NCH>& eh) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int S = q.S, j = i + d, lane = lane_id(), NM = w.n_max;
   const bool ne = LC.en.no_ene != 0;
   const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
@@ -1236,7 +1236,7 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
     bool c2P = gB;
     double tsc = 0., f0 = 1., f1 = 1.;
     if (gB && !ne) {
-      tsc = nl_e_ext(&q, i, j - 1, 0) + LC.en.mlintern;
+      tsc = nl_e_ext(&c.q, i, j - 1, 0) + LC.en.mlintern;
       c2P = tsc > NINF;
       if (c2P) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
     }
@@ -1259,7 +1259,7 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
     bool cPP = true;
     double tsc = 0., f0 = 1., f1 = 1.;
     if (!ne) {
-      tsc = nl_e_loop(&q, i - 1, j, i, j - 1);
+      tsc = nl_e_loop(&c.q, i - 1, j, i, j - 1);
       cPP = tsc > NINF;
       if (cPP) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
     }
@@ -1294,7 +1294,7 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
     bool cX = true;
     double tsc = 0., f0 = 1., f1 = 1.;
     if (!ne) {
-      tsc = nl_e_ext(&q, i, j - 1, 1);
+      tsc = nl_e_ext(&c.q, i, j - 1, 1);
       cX = tsc > NINF;
       if (cX) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
     }
@@ -1363,7 +1363,7 @@ template <int NCH>
 RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, WarpLin& w, EhAcc<NCH>& eh) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int S = q.S, j = i + d, lane = lane_id(), L = q.L, W = q.W, NM = w.n_max;
   const bool ne = LC.en.no_ene != 0;
   const unsigned il = cidx(q, i, d);
@@ -1372,7 +1372,7 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
     bool cH = gE;
     double tH = 0., h0 = 1., h1 = 1.;
     if (gE && !ne) {
-      tH = nl_e_hairpin(&q, i - 1, j);
+      tH = nl_e_hairpin(&c.q, i - 1, j);
       cH = tH > NINF;
       if (cH) { F2 ff = boltz2(tH); h0 = ff.f0; h1 = ff.f1; }
     }
@@ -1484,7 +1484,7 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
 
 // one diagonal of the outside pass, phase-major over the warp's cells
 template <int NCH> RDEV void lin_outside_diag(const LinCtx& c, const CTabs& t, int d, WarpLin& w, EhAcc<NCH>& eh) {
-  const SeqView& q = c.q;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
   const int ncell = q.L + 1 - d, w0 = warp_id(), nw = n_warps();
   if (d >= 3)
     for (int i = w0; i < ncell; i += nw) {
