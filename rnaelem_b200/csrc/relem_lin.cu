@@ -264,7 +264,7 @@ template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot
 // grid = count * ntile CTAs; CTA (sk, tk) owns cells [tk*tile, (tk+1)*tile) of diagonal d of sequence slot sk,
 // its warps take them interleaved
 template <int PH, int NCH>
-LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 5)) relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
+LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 7)) relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
