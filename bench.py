@@ -263,8 +263,10 @@ def main_own(args):
     ctx.estep(*pn)
     barrier()
     t2 = time.perf_counter()
+    e2e_kernel_ms = []
     for _ in range(args.steps):
         r = ctx.estep(*pn)
+        e2e_kernel_ms.append(sum(t[1] for t in ctx.timing() if t[2] > 0))
         if world > 1:
             ctx.allreduce_sum(np.concatenate([[r.fn, r.sum_eff, float(r.n_skipped)], r.EN_diff, r.EH_diff]))
     barrier()
@@ -293,7 +295,8 @@ def main_own(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(npos, world),
                 "seq_evals_per_s": world * 2 * npos * args.steps / dt,
-                "e2e": {"value": e2e, "unit": "dp_cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "e2e": {"value": e2e, "unit": "dp_cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": 1e3 * dt_e2e / args.steps, "kernel_ms_per_step": float(np.mean(e2e_kernel_ms))},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,

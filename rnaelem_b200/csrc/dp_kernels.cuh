@@ -279,34 +279,51 @@ RELEM_KERNEL relem_estep_kernel(ModelView nullm, ModelView m, BatchView b, SlotL
 
 // batch reduction (the per-thread accumulate + mutex block of motif_trainer.hpp:248-271, made deterministic):
 // res = [fn, sum_eff, n_skipped, EHo0, EHo1, EHx0, EHx1, ENo[NT], ENx[NT]]
-RELEM_KERNEL relem_reduce_kernel(int nseq, int NT, const unsigned char* kind, const int* gate, EstepOut out,
-                                 double* res RELEM_SMEM_ARG) {
+// step 1: a gated sequence (the negative of a skipped positive) is dropped with its gate
+RELEM_KERNEL relem_gate_kernel(int nseq, const int* gate, EstepOut out RELEM_SMEM_ARG) {
 #ifdef RELEM_HOST_EMU
   (void)smem_raw;
+  for (int n = 0; n < nseq; ++n) {
+#else
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < nseq; n += gridDim.x * blockDim.x) {
 #endif
-  // resolve gates first (a gated sequence is dropped when its gate was skipped)
-  for (int n = CTA_TID; n < nseq; n += CTA_NTH) {
     int g = gate ? gate[n] : -1;
-    if (g >= 0 && out.skipped[g] == 1 && out.skipped[n] != 1) out.skipped[n] = 2;
-    else if (g >= 0 && out.skipped[g] == 1) out.skipped[n] = 2;
+    if (g >= 0 && out.skipped[g] == 1) out.skipped[n] = 2;
   }
+}
+// step 2: one CTA per output; thread p sums sequences p, p+T, ... and a fixed-shape tree adds the partial sums, so
+// the result does not depend on scheduling
+RELEM_KERNEL relem_reduce_kernel(int nseq, int NT, const unsigned char* kind, EstepOut out, double* res,
+                                 int emu_block RELEM_SMEM_ARG) {
+#ifdef RELEM_HOST_EMU
+  (void)smem_raw;
+  const int t = emu_block;
+  double red1[1];
+  double* red = red1;
+#else
+  (void)emu_block;
+  const int t = (int)blockIdx.x;
+  __shared__ double red[RELEM_CTA_THREADS];
+#endif
+  double acc = 0.;
+  for (int n = CTA_TID; n < nseq; n += CTA_NTH) {
+    int sk = out.skipped[n];
+    if (t == 2) { if (sk == 1) acc += 1.; continue; }
+    if (sk) continue;
+    int kd = kind[n];
+    if (t == 0) acc += out.Z[n * 3 + 0] - (kd == 1 ? out.Z[n * 3 + 1] : out.Z[n * 3 + 2]);
+    else if (t == 1) { if (kd != 2) acc += out.bpp_eff[n]; }
+    else if (t < 7) acc += out.EH[n * 4 + (t - 3)];
+    else if (t < 7 + NT) acc += out.ENo[(long long)n * NT + (t - 7)];
+    else acc += out.ENx[(long long)n * NT + (t - 7 - NT)];
+  }
+  red[CTA_TID] = acc;
   CTA_SYNC();
-  int nout = 7 + 2 * NT;
-  for (int t = CTA_TID; t < nout; t += CTA_NTH) {
-    double acc = 0.;
-    for (int n = 0; n < nseq; ++n) {
-      int sk = out.skipped[n];
-      if (t == 2) { if (sk == 1) acc += 1.; continue; }
-      if (sk) continue;
-      int kd = kind[n];
-      if (t == 0) acc += out.Z[n * 3 + 0] - (kd == 1 ? out.Z[n * 3 + 1] : out.Z[n * 3 + 2]);
-      else if (t == 1) { if (kd != 2) acc += out.bpp_eff[n]; }
-      else if (t < 7) acc += out.EH[n * 4 + (t - 3)];
-      else if (t < 7 + NT) acc += out.ENo[(long long)n * NT + (t - 7)];
-      else acc += out.ENx[(long long)n * NT + (t - 7 - NT)];
-    }
-    res[t] = acc;
+  for (int o = CTA_NTH / 2; o > 0; o >>= 1) {
+    if (CTA_TID < o) red[CTA_TID] += red[CTA_TID + o];
+    CTA_SYNC();
   }
+  if (CTA_TID == 0) res[t] = red[0];
 }
 
 // -------------------------------------------------------------------------------------------------- bpp

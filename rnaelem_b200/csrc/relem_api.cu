@@ -110,6 +110,7 @@ struct relem_ctx {
   lin::LinHMM dlh;
   lin::LinParams dlp;
   lin::LinState* lin = nullptr;
+  relem_batch* staging = nullptr;      // reused by the host-buffer entry points
   DevBuf d_energy_lin, d_lin_ints, d_lin_w, d_flag, d_order2;
   bool have_lin = false;
   DevHMM dh, dnull;
@@ -375,6 +376,7 @@ void relem_destroy(relem_ctx* c) {
   c->d_coll.release();
 #endif
   if (c->lin) lin::lin_state_destroy(c->lin);
+  if (c->staging) relem_batch_destroy(c, c->staging);
   DevBuf* all[] = {&c->d_energy_lin, &c->d_lin_ints, &c->d_lin_w, &c->d_flag, &c->d_order2, &c->d_prof, &c->d_energy, &c->d_codes, &c->d_hmm, &c->d_null, &c->d_n2s, &c->d_theta, &c->d_null_theta,
                    &c->d_scratch, &c->d_queue, &c->d_res, &c->d_Z, &c->d_ENo, &c->d_ENx, &c->d_EH, &c->d_eff,
                    &c->d_skip, &c->d_s1, &c->d_s2, &c->d_s3, &c->d_s4, &c->d_s5, &c->d_s6, &c->d_s7, &c->d_s8,
@@ -529,26 +531,26 @@ int relem_set_params(relem_ctx* c, const double* theta_flat, int n_theta, const 
   return RELEM_OK;
 }
 
-int relem_batch_create(relem_ctx* c, int nseq, const uint8_t* seq_cat, const int64_t* off, const double* ws_cat,
-                       const uint8_t* kind, const int32_t* gate, relem_batch** out) {
-  if (!c || !out || nseq < 0 || !off || (nseq > 0 && (!seq_cat || !ws_cat))) return RELEM_EINVAL;
+static int batch_fill(relem_ctx* c, relem_batch* b, int nseq, const uint8_t* seq_cat, const int64_t* off,
+                      const double* ws_cat, const uint8_t* kind, const int32_t* gate) {
+  if (!c || !b || nseq < 0 || !off || (nseq > 0 && (!seq_cat || !ws_cat))) return RELEM_EINVAL;
   if (!c->have_energy) return fail(c, RELEM_EINVAL, "relem_set_energy has not been called");
-  relem_batch* b = new relem_batch();
+  b->Lmax = 0; b->cells = 0; b->has_gate = false;
   b->nseq = nseq;
   b->off.assign(off, off + nseq + 1);
   b->total_len = off[nseq] - off[0];
-  if (off[0] != 0) { delete b; return fail(c, RELEM_EINVAL, "off[0] must be 0"); }
+  if (off[0] != 0) { return fail(c, RELEM_EINVAL, "off[0] must be 0"); }
   std::vector<int> order(nseq);
   std::iota(order.begin(), order.end(), 0);
   for (int n = 0; n < nseq; ++n) {
     long long L = off[n + 1] - off[n];
-    if (L < 1 || L > 9999) { delete b; return fail(c, RELEM_EINVAL, "sequence length must be in 1..9999"); }
+    if (L < 1 || L > 9999) { return fail(c, RELEM_EINVAL, "sequence length must be in 1..9999"); }
     b->Lmax = std::max<int>(b->Lmax, (int)L);
     long long W = std::min<long long>(L, c->max_span);
     b->cells += (L + 1) * (W + 1) - W * (W + 1) / 2;
   }
   for (long long k = 0; k < b->total_len; ++k)
-    if (seq_cat[k] > 4) { delete b; return fail(c, RELEM_EINVAL, "base codes must be 0..4"); }
+    if (seq_cat[k] > 4) { return fail(c, RELEM_EINVAL, "base codes must be 0..4"); }
   std::stable_sort(order.begin(), order.end(),
                    [&](int a, int bb) { return off[a + 1] - off[a] > off[bb + 1] - off[bb]; });
   b->kind.assign(nseq, 0);
@@ -556,17 +558,27 @@ int relem_batch_create(relem_ctx* c, int nseq, const uint8_t* seq_cat, const int
   b->gate.assign(nseq, -1);
   if (gate) { b->gate.assign(gate, gate + nseq); b->has_gate = true; }
   for (int n = 0; n < nseq; ++n) {
-    if (b->kind[n] > 2) { delete b; return fail(c, RELEM_EINVAL, "bad sequence kind"); }
-    if (b->gate[n] >= nseq || b->gate[n] == n) { delete b; return fail(c, RELEM_EINVAL, "bad gate index"); }
+    if (b->kind[n] > 2) { return fail(c, RELEM_EINVAL, "bad sequence kind"); }
+    if (b->gate[n] >= nseq || b->gate[n] == n) { return fail(c, RELEM_EINVAL, "bad gate index"); }
   }
-  std::vector<unsigned char> seqv(seq_cat, seq_cat + b->total_len);
-  std::vector<double> wsv(ws_cat, ws_cat + b->total_len);
+  // the caller's buffers go to the device as they are (no staging copies)
   std::vector<long long> offv(off, off + nseq + 1);
-  if (!upload(b->d_seq, seqv) || !upload(b->d_ws, wsv) || !upload(b->d_off, offv) || !upload(b->d_kind, b->kind) ||
+  const size_t nb = (size_t)b->total_len;
+  bool up = b->d_seq.reserve(nb) && Dev::h2d(b->d_seq.p, seq_cat, nb) && b->d_ws.reserve(nb * sizeof(double)) &&
+            Dev::h2d(b->d_ws.p, ws_cat, nb * sizeof(double));
+  if (!up || !upload(b->d_off, offv) || !upload(b->d_kind, b->kind) ||
       !upload(b->d_gate, b->gate) || !upload(b->d_order, order)) {
-    relem_batch_destroy(c, b);
     return fail(c, RELEM_ENOMEM, "batch upload failed");
   }
+  return RELEM_OK;
+}
+
+int relem_batch_create(relem_ctx* c, int nseq, const uint8_t* seq_cat, const int64_t* off, const double* ws_cat,
+                       const uint8_t* kind, const int32_t* gate, relem_batch** out) {
+  if (!out) return RELEM_EINVAL;
+  relem_batch* b = new relem_batch();
+  int rc = batch_fill(c, b, nseq, seq_cat, off, ws_cat, kind, gate);
+  if (rc) { relem_batch_destroy(c, b); return rc; }
   *out = b;
   return RELEM_OK;
 }
@@ -669,11 +681,13 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
   bv = batch_view(b);
   {
     Timer t(c, "relem_reduce_kernel");
+    const int* gp = b->has_gate ? b->d_gate.as<int>() : nullptr;
 #ifdef RELEM_HOST_EMU
-    relem_reduce_kernel(nseq, NT, bv.kind, b->has_gate ? b->d_gate.as<int>() : nullptr, eo, c->d_res.as<double>(), nullptr);
+    relem_gate_kernel(nseq, gp, eo, nullptr);
+    for (int k = 0; k < nres; ++k) relem_reduce_kernel(nseq, NT, bv.kind, eo, c->d_res.as<double>(), k, nullptr);
 #else
-    relem_reduce_kernel<<<1, RELEM_CTA_THREADS, 0, c->stream>>>(nseq, NT, bv.kind, b->has_gate ? b->d_gate.as<int>() : nullptr, eo,
-                                                  c->d_res.as<double>());
+    relem_gate_kernel<<<std::max(1, std::min(1024, (nseq + 127) / 128)), RELEM_CTA_THREADS, 0, c->stream>>>(nseq, gp, eo);
+    relem_reduce_kernel<<<nres, RELEM_CTA_THREADS, 0, c->stream>>>(nseq, NT, bv.kind, eo, c->d_res.as<double>(), 0);
     CUDA_TRY(c, cudaGetLastError());
 #endif
     t.stop();
@@ -709,12 +723,13 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
 
 int relem_estep(relem_ctx* c, int nseq, const uint8_t* seq_cat, const int64_t* off, const double* ws_cat,
                 const uint8_t* kind, const int32_t* gate, relem_estep_out* out) {
-  relem_batch* b = nullptr;
-  int rc = relem_batch_create(c, nseq, seq_cat, off, ws_cat, kind, gate, &b);
+  if (!c) return RELEM_EINVAL;
+  // the staging batch lives in the context: its device buffers only grow, so a training loop that calls this
+  // once per iteration pays for the copies, not for allocations
+  if (!c->staging) c->staging = new relem_batch();
+  int rc = batch_fill(c, c->staging, nseq, seq_cat, off, ws_cat, kind, gate);
   if (rc) return rc;
-  rc = relem_estep_run(c, b, out);
-  relem_batch_destroy(c, b);
-  return rc;
+  return relem_estep_run(c, c->staging, out);
 }
 
 int relem_bpp(relem_ctx* c, relem_batch* b, int64_t* moff, uint8_t* bp_ok, uint8_t* left_ok, double* lnbpp,

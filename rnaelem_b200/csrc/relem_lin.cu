@@ -523,6 +523,10 @@ struct LinState {
   size_t scratch_bytes = 0;
   void* k0pow = nullptr;
   size_t k0pow_n = 0;
+#ifndef RELEM_HOST_EMU
+  cudaStream_t lane[2] = {nullptr, nullptr};  // two chunks in flight: one fills the SMs while the other's kernel drains
+  cudaEvent_t lane_done[2] = {nullptr, nullptr};
+#endif
 };
 
 LinState* lin_state_create() { return new LinState(); }
@@ -533,6 +537,10 @@ void lin_state_destroy(LinState* s) {
 #else
   if (s->scratch) cudaFree(s->scratch);
   if (s->k0pow) cudaFree(s->k0pow);
+  for (int k = 0; k < 2; ++k) {
+    if (s->lane[k]) cudaStreamDestroy(s->lane[k]);
+    if (s->lane_done[k]) cudaEventDestroy(s->lane_done[k]);
+  }
 #endif
   delete s;
 }
@@ -653,10 +661,16 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   long long by_mem = (long long)(((double)(free_b + st->scratch_bytes) * 0.70) / (double)per);
-  long long nslots = std::min<long long>(nseq, by_mem);
-  if (in.max_slots > 0) nslots = std::min<long long>(nslots, in.max_slots);
-  if (nslots < 1) { err = "not enough device memory for one sequence slot"; return 3; }
-  size_t need = (size_t)nslots * per;
+  if (in.max_slots > 0) by_mem = std::min<long long>(by_mem, in.max_slots);
+  if (by_mem < 1) { err = "not enough device memory for one sequence slot"; return 3; }
+  // two lanes (streams) with half of the slots each once there is enough work to keep both busy
+  const int nlanes = (nseq >= 4096 && by_mem >= 2048) ? 2 : 1;
+  long long nslots = std::min<long long>((nseq + nlanes - 1) / nlanes, by_mem / nlanes);
+  // keep an existing scratch buffer when it is close to what we would ask for (free memory fluctuates a little
+  // from call to call; re-allocating ~100 GB costs more than a slightly smaller chunk)
+  const long long have = (long long)(st->scratch_bytes / ((size_t)nlanes * per));
+  if (have >= 1 && have < nslots && have * 10 >= nslots * 8) nslots = have;
+  size_t need = (size_t)nslots * nlanes * per;
   if (need > st->scratch_bytes) {
     if (st->scratch) cudaFree(st->scratch);
     st->scratch = nullptr; st->scratch_bytes = 0;
@@ -675,15 +689,34 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   if (e == cudaSuccess) e = cudaStreamSynchronize(r.stream);  // kp / hc are stack objects
   if (e != cudaSuccess) { err = std::string("constant upload: ") + cudaGetErrorString(e); return 2; }
   a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
+  cudaStream_t main_stream = r.stream;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  cudaEventRecord(e0, r.stream);
   LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
-  for (int base = 0; base < nseq; base += (int)nslots) {
+  cudaEventRecord(e0, main_stream);
+  if (nlanes == 2) {
+    for (int k = 0; k < 2; ++k) {
+      if (!st->lane[k]) cudaStreamCreateWithFlags(&st->lane[k], cudaStreamNonBlocking);
+      if (!st->lane_done[k]) cudaEventCreateWithFlags(&st->lane_done[k], cudaEventDisableTiming);
+      cudaStreamWaitEvent(st->lane[k], e0, 0);
+    }
+  }
+  int chunk = 0;
+  for (int base = 0; base < nseq; base += (int)nslots, ++chunk) {
+    const int ln = nlanes == 2 ? (chunk & 1) : 0;
+    r.stream = nlanes == 2 ? st->lane[ln] : main_stream;
+    a.scratch = (double*)st->scratch + (size_t)ln * (size_t)nslots * lay.stride;
     a.base = base; a.count = std::min<int>((int)nslots, nseq - base);
     if (in.nch == 2) run_chunk<2>(r, in.en.filter != 0, NT);
     else run_chunk<1>(r, in.en.filter != 0, NT);
   }
+  if (nlanes == 2) {
+    for (int k = 0; k < 2; ++k) {
+      cudaEventRecord(st->lane_done[k], st->lane[k]);
+      cudaStreamWaitEvent(main_stream, st->lane_done[k], 0);
+    }
+  }
+  r.stream = main_stream;
   e = cudaGetLastError();
   cudaEventRecord(e1, r.stream);
   if (e != cudaSuccess) { err = std::string("linear-space kernel launch: ") + cudaGetErrorString(e); return 2; }
