@@ -134,6 +134,7 @@ RDEV void cta_right_mask(const SeqView& q, const unsigned* byleft, unsigned* byr
 RDEV bool finite_pos(double v) { return v > 0. && v < (-NINF); }
 
 // the CTA's view of sequence slot `sk`: LinCtx in shared memory pointing at the slot header
+template <bool FROM_HDR = true>
 RDEV LinCtx& lin_attach(const LinKArgs& a, unsigned char* smem_raw, int sk, double*& slot, int& n) {
   const LinLayout& lay = a.lay;
   LinCtx& c = *(LinCtx*)(smem_raw + lay.sm_ctx);
@@ -141,7 +142,8 @@ RDEV LinCtx& lin_attach(const LinKArgs& a, unsigned char* smem_raw, int sk, doub
   n = a.b.order[a.base + sk];
   if (CTA_TID == 0) {
     const long long o = a.b.off[n];
-    const int L = (int)(a.b.off[n + 1] - o);
+    // the prep kernel leaves the length in the header: one dependent load less on the critical path of every CTA
+    const int L = FROM_HDR ? (int)slot[lay.hdr + 5] : (int)(a.b.off[n + 1] - o);
     const int W = L < LC.en.max_span ? L : LC.en.max_span;
     const int C = W - 7 < LC.en.max_iloop ? W - 7 : LC.en.max_iloop;
     SeqView& q = c.q;
@@ -207,7 +209,7 @@ LIN_KERNEL(LIN_THREADS, 8) relem_lin_prep_kernel(LinKArgs a LIN_SMEM_ARG) {
   const int sk = LIN_BLOCK_IDX;
   if (sk >= a.count) return;
   double* slot; int n;
-  LinCtx& c = lin_attach(a, smem_raw, sk, slot, n);
+  LinCtx& c = lin_attach<false>(a, smem_raw, sk, slot, n);
   const SeqView& q = c.q;
   const int L = q.L;
   const long long o = a.b.off[n];
@@ -230,6 +232,7 @@ LIN_KERNEL(LIN_THREADS, 8) relem_lin_prep_kernel(LinKArgs a LIN_SMEM_ARG) {
   cta_right_mask(q, lf, mk + 3 * lay.mask_words);
   if (CTA_TID == 0) {
     slot[lay.hdr + 4] = (double)total;
+    slot[lay.hdr + 5] = (double)L;
     a.out.bpp_eff[n] = 1.;
   }
 }
@@ -524,8 +527,8 @@ struct LinState {
   void* k0pow = nullptr;
   size_t k0pow_n = 0;
 #ifndef RELEM_HOST_EMU
-  cudaStream_t lane[2] = {nullptr, nullptr};  // two chunks in flight: one fills the SMs while the other's kernel drains
-  cudaEvent_t lane_done[2] = {nullptr, nullptr};
+  cudaStream_t lane[4] = {nullptr, nullptr, nullptr, nullptr};  // two chunks in flight: one fills the SMs while the other's kernel drains
+  cudaEvent_t lane_done[4] = {nullptr, nullptr, nullptr, nullptr};
 #endif
 };
 
@@ -537,7 +540,7 @@ void lin_state_destroy(LinState* s) {
 #else
   if (s->scratch) cudaFree(s->scratch);
   if (s->k0pow) cudaFree(s->k0pow);
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 4; ++k) {
     if (s->lane[k]) cudaStreamDestroy(s->lane[k]);
     if (s->lane_done[k]) cudaEventDestroy(s->lane_done[k]);
   }
@@ -550,6 +553,7 @@ struct Runner {
   LinKArgs a;
   int smem_in, smem_out, smem_small, smem_k0, smem_ext_in, smem_ext_out;
   int launches = 0;
+  int tile_k0 = 32, tile_d = 64;   // cells per CTA of the dense phases (measured sweet spot, RELEM_TILE_*)
 #ifdef RELEM_HOST_EMU
   std::vector<unsigned char> smem;
 #else
@@ -583,17 +587,17 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
   const int W = r.a.lay.Wmax, cnt = r.a.count;
   LIN_LAUNCH(r, relem_lin_prep_kernel, cnt, LIN_THREADS, r.smem_small);
   if (filter) {
-    for (int d = 3; d <= W; ++d) launch_phase<PH_K0_IN, 1>(r, d, 32, r.smem_k0);
+    for (int d = 3; d <= W; ++d) launch_phase<PH_K0_IN, 1>(r, d, r.tile_k0, r.smem_k0);
     LIN_LAUNCH(r, (relem_lin_ext_kernel<0, 1>), cnt, 32, r.smem_small);
     LIN_LAUNCH(r, (relem_lin_ext_kernel<1, 1>), cnt, 32, r.smem_small);
-    for (int d = W; d >= 3; --d) launch_phase<PH_K0_OUT, 1>(r, d, 32, r.smem_k0);
+    for (int d = W; d >= 3; --d) launch_phase<PH_K0_OUT, 1>(r, d, r.tile_k0, r.smem_k0);
     LIN_LAUNCH(r, relem_lin_filter_kernel, cnt, LIN_THREADS, r.smem_small);
   }
   for (int d = 0; d <= W; ++d) {
-    launch_phase<PH_IN_L, 1>(r, d, 32, r.smem_in);
+    launch_phase<PH_IN_L, 1>(r, d, r.tile_d, r.smem_in);
     if (d >= 5) {
       launch_phase<PH_IN_P, 1>(r, d, 64, r.smem_in);
-      launch_phase<PH_IN_B, 1>(r, d, 32, r.smem_in);
+      launch_phase<PH_IN_B, 1>(r, d, r.tile_d, r.smem_in);
     }
     if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, 128, r.smem_in);
   }
@@ -602,10 +606,10 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
   for (int d = W; d >= 0; --d) {
     if (d >= 3) launch_phase<PH_OUT_EM, NCH>(r, d, 64, r.smem_out);
     if (d >= 5) {
-      launch_phase<PH_OUT_B, NCH>(r, d, 32, r.smem_out);
+      launch_phase<PH_OUT_B, NCH>(r, d, r.tile_d, r.smem_out);
       launch_phase<PH_OUT_P, NCH>(r, d, 128, r.smem_out);
     }
-    launch_phase<PH_OUT_L, NCH>(r, d, 32, r.smem_out);
+    launch_phase<PH_OUT_L, NCH>(r, d, r.tile_d, r.smem_out);
   }
   LIN_LAUNCH(r, (relem_lin_fold_kernel<NCH>), cnt, LIN_THREADS, NCH * NT * 8 + 16);
 }
@@ -628,6 +632,8 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   r.smem_ext_in = lay.sm_warp + lay.warp_bytes_in;
   r.smem_ext_out = lay.sm_warp + lay.warp_bytes_out;
   const int NT = in.p.n_theta;
+  if (const char* e = std::getenv("RELEM_TILE_K0")) r.tile_k0 = std::max(4, std::atoi(e));
+  if (const char* e = std::getenv("RELEM_TILE_D")) r.tile_d = std::max(4, std::atoi(e));
   // kappa0 powers [0, KP) followed by the separable interior-loop table G[32][32]; the device fills G (gtab kernel)
   const int KP = std::max(256, (lay.Wmax + 3 + 31) & ~31);
   std::vector<double> kp(KP + 1024, 0.);
@@ -664,7 +670,8 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   if (in.max_slots > 0) by_mem = std::min<long long>(by_mem, in.max_slots);
   if (by_mem < 1) { err = "not enough device memory for one sequence slot"; return 3; }
   // two lanes (streams) with half of the slots each once there is enough work to keep both busy
-  const int nlanes = (nseq >= 4096 && by_mem >= 2048) ? 2 : 1;
+  int nlanes = (nseq >= 4096 && by_mem >= 2048) ? 2 : 1;
+  if (const char* e = std::getenv("RELEM_LANES")) nlanes = std::max(1, std::min(4, std::atoi(e)));
   long long nslots = std::min<long long>((nseq + nlanes - 1) / nlanes, by_mem / nlanes);
   // keep an existing scratch buffer when it is close to what we would ask for (free memory fluctuates a little
   // from call to call; re-allocating ~100 GB costs more than a slightly smaller chunk)
@@ -694,8 +701,8 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
   cudaEventRecord(e0, main_stream);
-  if (nlanes == 2) {
-    for (int k = 0; k < 2; ++k) {
+  if (nlanes >= 2) {
+    for (int k = 0; k < nlanes; ++k) {
       if (!st->lane[k]) cudaStreamCreateWithFlags(&st->lane[k], cudaStreamNonBlocking);
       if (!st->lane_done[k]) cudaEventCreateWithFlags(&st->lane_done[k], cudaEventDisableTiming);
       cudaStreamWaitEvent(st->lane[k], e0, 0);
@@ -703,15 +710,15 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   }
   int chunk = 0;
   for (int base = 0; base < nseq; base += (int)nslots, ++chunk) {
-    const int ln = nlanes == 2 ? (chunk & 1) : 0;
-    r.stream = nlanes == 2 ? st->lane[ln] : main_stream;
+    const int ln = chunk % nlanes;
+    r.stream = nlanes >= 2 ? st->lane[ln] : main_stream;
     a.scratch = (double*)st->scratch + (size_t)ln * (size_t)nslots * lay.stride;
     a.base = base; a.count = std::min<int>((int)nslots, nseq - base);
     if (in.nch == 2) run_chunk<2>(r, in.en.filter != 0, NT);
     else run_chunk<1>(r, in.en.filter != 0, NT);
   }
-  if (nlanes == 2) {
-    for (int k = 0; k < 2; ++k) {
+  if (nlanes >= 2) {
+    for (int k = 0; k < nlanes; ++k) {
       cudaEventRecord(st->lane_done[k], st->lane[k]);
       cudaStreamWaitEvent(main_stream, st->lane_done[k], 0);
     }
