@@ -444,8 +444,8 @@ struct CTabs {
 };
 
 struct WarpLin {
-  double* curA;   // [NPLANE][S] inside values of the current cell
-  double* curB;   // [NCH][NPLANE][S] outside values of the current cell
+  double* curA;   // [S] staging of the current cell (inside: B; exterior rows)
+  double* curB;   // [NCH][S] outside values of the state type being gathered
   double* partA;  // [NCH][n_max] per-entry partial sums
   double* partT;  // [NCH][n_max] per-entry partial sums weighted by the transition energy
   int *bi, *bj;   // candidate buffer
@@ -459,16 +459,16 @@ struct WarpLin {
 };
 // inside = true: only what the inside pass needs (no outside staging, no counts)
 RHD int warp_lin_bytes(int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside) {
-  int n = inside ? (NPLANE * S + n_max + 3 * LIN_CAP) * 8
-                 : (NPLANE * S + nch * NPLANE * S + 2 * nch * n_max + 3 * LIN_CAP + nch * 5 * (n_right + n_left)) * 8;
+  int n = inside ? (S + n_max + 3 * LIN_CAP) * 8
+                 : (S + nch * S + 2 * nch * n_max + 3 * LIN_CAP + nch * 5 * (n_right + n_left)) * 8;
   n += (2 * LIN_CAP + Wmax + 4) * 4;
   return (n + 15) & ~15;
 }
 RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside) {
   WarpLin w;
   double* p = (double*)base;
-  w.curA = p; p += NPLANE * S;
-  w.curB = p; p += inside ? 0 : nch * NPLANE * S;
+  w.curA = p; p += S;
+  w.curB = p; p += inside ? 0 : nch * S;
   w.partA = p; p += inside ? n_max : nch * n_max;
   w.partT = p; p += inside ? 0 : nch * n_max;
   w.bt = p; p += LIN_CAP;

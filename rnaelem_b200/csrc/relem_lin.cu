@@ -553,6 +553,7 @@ struct Runner {
   LinKArgs a;
   int smem_in, smem_out, smem_small, smem_k0, smem_ext_in, smem_ext_out;
   int launches = 0;
+  int tile_p = 128, tile_e = 256;   // cells per CTA of the phases that touch few cells
   int tile_k0 = 32, tile_d = 64;   // cells per CTA of the dense phases (measured sweet spot, RELEM_TILE_*)
 #ifdef RELEM_HOST_EMU
   std::vector<unsigned char> smem;
@@ -596,18 +597,18 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
   for (int d = 0; d <= W; ++d) {
     launch_phase<PH_IN_L, 1>(r, d, r.tile_d, r.smem_in);
     if (d >= 5) {
-      launch_phase<PH_IN_P, 1>(r, d, 64, r.smem_in);
+      launch_phase<PH_IN_P, 1>(r, d, r.tile_p, r.smem_in);
       launch_phase<PH_IN_B, 1>(r, d, r.tile_d, r.smem_in);
     }
-    if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, 128, r.smem_in);
+    if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, r.tile_e, r.smem_in);
   }
   LIN_LAUNCH(r, (relem_lin_ext_kernel<2, NCH>), cnt, 32, r.smem_ext_in);
   LIN_LAUNCH(r, (relem_lin_ext_kernel<3, NCH>), cnt, 32, r.smem_ext_out);
   for (int d = W; d >= 0; --d) {
-    if (d >= 3) launch_phase<PH_OUT_EM, NCH>(r, d, 64, r.smem_out);
+    if (d >= 3) launch_phase<PH_OUT_EM, NCH>(r, d, r.tile_p, r.smem_out);
     if (d >= 5) {
       launch_phase<PH_OUT_B, NCH>(r, d, r.tile_d, r.smem_out);
-      launch_phase<PH_OUT_P, NCH>(r, d, 128, r.smem_out);
+      launch_phase<PH_OUT_P, NCH>(r, d, r.tile_e, r.smem_out);
     }
     launch_phase<PH_OUT_L, NCH>(r, d, r.tile_d, r.smem_out);
   }
@@ -634,6 +635,8 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   const int NT = in.p.n_theta;
   if (const char* e = std::getenv("RELEM_TILE_K0")) r.tile_k0 = std::max(4, std::atoi(e));
   if (const char* e = std::getenv("RELEM_TILE_D")) r.tile_d = std::max(4, std::atoi(e));
+  if (const char* e = std::getenv("RELEM_TILE_P")) r.tile_p = std::max(4, std::atoi(e));
+  if (const char* e = std::getenv("RELEM_TILE_E")) r.tile_e = std::max(4, std::atoi(e));
   // kappa0 powers [0, KP) followed by the separable interior-loop table G[32][32]; the device fills G (gtab kernel)
   const int KP = std::max(256, (lay.Wmax + 3 + 31) & ~31);
   std::vector<double> kp(KP + 1024, 0.);
