@@ -272,6 +272,18 @@ def main_own(args):
     barrier()
     dt_e2e = time.perf_counter() - t2
 
+    # secondary figure of BASELINE.json's metric: `elem scan` sequences/s (posteriors on the linear-space kernels,
+    # bit-exact Viterbi on the log-space kernel), on a bounded sample of the same sequences
+    nscan = min(2 * npos, 2048)
+    sb = ctx.batch(seq_cat[:nscan * SEQ_LEN], off[:nscan + 1], ws[:nscan * SEQ_LEN])
+    ctx.scan_run(sb)
+    barrier()
+    t3 = time.perf_counter()
+    ctx.scan_run(sb)
+    barrier()
+    dt_scan = time.perf_counter() - t3
+    sb.close()
+
     if dist is not None:
         t = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -303,7 +315,8 @@ def main_own(args):
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": which,
                              "kernel_ms": kms, "algorithmic_bytes_per_launch": int(step_bytes),
                              "note": "one 'launch' = the whole wavefront of phase kernels over the step's batch"},
-                "phase_share": phases}
+                "phase_share": phases,
+                "scan": {"value": world * nscan / dt_scan, "unit": "seqs/s", "sample": "%d x %d nt per GPU" % (nscan, SEQ_LEN)}}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             line["cpu_baseline"] = cpu_baseline(args.ref_sample or max(16, 4 * cores))

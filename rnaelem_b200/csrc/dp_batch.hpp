@@ -25,6 +25,12 @@ struct EstepOut {   // device arrays, per sequence
   unsigned long long* prof;  // [16] cycles per phase summed over CTAs (thread 0 clocks), may be null
 };
 
+// device arrays of the scanner's results (sequence n at off[n]; PyeL at off[n]+n)
+struct ScanOut {
+  double* PysL; double* PyeL; double* PyiL;
+  int* psihat; char* rss; int* Ys; int* Ye; double* exist; double* EN /*[nseq][n_theta]*/; double* ZL;
+};
+
 }  // namespace dp
 }  // namespace relem
 #endif

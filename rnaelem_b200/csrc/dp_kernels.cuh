@@ -24,11 +24,6 @@ struct SlotLayout {
       sm_total;
 };
 
-struct ScanOut {
-  double* PysL; double* PyeL; double* PyiL;
-  int* psihat; char* rss; int* Ys; int* Ye; double* exist; double* EN /*[nseq][n_theta]*/; double* ZL;
-};
-
 struct BppOut {
   const long long* moff;  // [nseq+1] byte offsets of the per-sequence masks
   unsigned char* bp_ok; unsigned char* left_ok; double* lnbpp; double* bpp_eff; double* lnZ;
@@ -524,6 +519,68 @@ RELEM_KERNEL relem_scan_kernel(ModelView nullm, ModelView m, BatchView b, SlotLa
     StartEndConstraint se; se.ys = Ys; se.ye = Ye;
     unsigned long long* trace = (unsigned long long*)Q0;
     unsigned long long* otrace = (unsigned long long*)QO0;
+    cta_inside<true, StartEndConstraint>(m, q, tab, otab, trace, otrace, se);
+    for (int t = CTA_TID; t < L; t += CTA_NTH) { out.psihat[o + t] = 0; out.rss[o + t] = ' '; }
+    CTA_SYNC();
+    if (CTA_TID == 0) {
+      double a = h.s0M2 >= 0 ? otab[L * S + h.s0M2] : NINF;
+      double c = h.s0M1 >= 0 ? otab[L * S + h.s0M1] : NINF;
+      int s0 = (a < c) ? h.s0M1 : h.s0M2;
+      if (s0 >= 0) trace_back(m, q, trace, otrace, n2s, (int*)(slot + lay.stack), s0, out.psihat + o, out.rss + o);
+    }
+    CTA_SYNC();
+  }
+}
+
+// -------------------------------------------------------------------------------------------- Viterbi only
+// Constrained Viterbi + traceback (calc_viterbi_alignment, motif_scanner.hpp:172-184) for sequences whose posteriors
+// (hence Ys / Ye) and base-pair masks were produced by the linear-space kernels: masks are read from the header of the
+// sequence's linear-space slot, Ys / Ye from the result arrays.
+struct ExtMasks {
+  const double* scratch;           // linear-space slots of the chunk
+  unsigned long long stride;       // doubles per slot
+  unsigned long long masks_off;    // offset of the bp / lf bit rows in a slot (doubles)
+  int mask_words;                  // words per mask
+  int base, count;                 // chunk = sequences order[base .. base+count), slot k <-> base+k
+};
+RELEM_KERNEL relem_viterbi_kernel(ModelView m, BatchView b, SlotLayout lay, double* scratch, int* queue, const int* n2s,
+                                  ScanOut out, ExtMasks em, const unsigned char* flag RELEM_SMEM_ARG) {
+#ifndef RELEM_HOST_EMU
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
+  Smem sm = carve(smem_raw, lay);
+  double* slot = scratch + (unsigned long long)RELEM_BLOCK_IDX * lay.stride;
+  const int S = m.h.S;
+  const DevHMM& h = m.h;
+  for (;;) {
+    int qi = claim(queue, (int*)(sm.red + 40));
+    if (qi >= em.count) break;
+    int n = b.order[em.base + qi];
+    if (flag[n]) continue;   // left the fp64 range in the linear-space pass: the full log-space kernel redoes it
+    SeqView q;
+    q.S = S;
+    long long o = b.off[n];
+    const int L = (int)(b.off[n + 1] - o);
+    const int W = L < m.en.max_span ? L : m.en.max_span;
+    const int C = W - 7 < m.en.max_iloop ? W - 7 : m.en.max_iloop;
+    q.L = L; q.W = W; q.C = C; q.W1 = W + 1; q.cells = (unsigned)(L + 1) * (unsigned)(W + 1);
+    q.mw = lay.mw; q.min_pair = 5; q.min_multi = 10;
+    q.x = sm.x; q.bp = sm.bp; q.lf = sm.lf; q.sp3 = sm.sp3; q.sp4 = sm.sp4; q.sp6 = sm.sp6;
+    q.ws = b.ws + o;
+    for (int t = CTA_TID; t < L; t += CTA_NTH) sm.x[t] = b.seq[o + t];
+    if (CTA_TID == 0) sm.x[L] = 0;
+    const unsigned* g = (const unsigned*)(em.scratch + (unsigned long long)qi * em.stride + em.masks_off);
+    for (int t = CTA_TID; t < (L + 1) * lay.mw; t += CTA_NTH) { sm.bp[t] = g[t]; sm.lf[t] = g[em.mask_words + t]; }
+    CTA_SYNC();
+    cta_special_hairpins(m.en, sm.x, L, sm.sp3, sm.sp4, sm.sp6);
+    double* emit0 = slot + lay.emit0; double* emitT = slot + lay.emitT;
+    q.emit0 = emit0; q.emitT = emitT;
+    cta_emit_tables(m, q, emit0, emitT);
+    CTA_SYNC();
+    double* tab = slot + lay.tabA; double* otab = slot + lay.otab;
+    StartEndConstraint se; se.ys = out.Ys[n]; se.ye = out.Ye[n];
+    unsigned long long* trace = (unsigned long long*)(slot + lay.Q0);
+    unsigned long long* otrace = (unsigned long long*)(slot + lay.QO0);
     cta_inside<true, StartEndConstraint>(m, q, tab, otab, trace, otrace, se);
     for (int t = CTA_TID; t < L; t += CTA_NTH) { out.psihat[o + t] = 0; out.rss[o + t] = ' '; }
     CTA_SYNC();

@@ -67,7 +67,27 @@ struct LinCtx {
   const double* wsf;    // exp(position weight) [L]
   const double* k0pow;  // kappa0^u, u = 0..W+1
   int Ceff;             // min(C, 30): loops longer than 30 have zero weight (energy_param.hpp:754-755)
+  // scanner: motif start fixed at position ys (-1: unconstrained), InsideEndFun / OutsideEndFun,
+  // motif_scanner.hpp:606-639,720-760; linear start / inner / end posteriors [L+1] each
+  int ys;
+  double *pys, *pyi, *pye;
 };
+
+// scanner hooks (motif_scanner.hpp:420-579 start / inner, :667-800 end).  MODE 0: trainer, 1: start pass, 2: end pass
+template <int MODE> RDEV void hook_emit(const LinCtx& c, int fl, int pos, double post) {
+  if (MODE == 1) {
+    if (fl & LIN_F_START) red_add(c.pys + pos, post);
+    if (fl & LIN_F_INNER) red_add(c.pyi + pos, post);
+  }
+  if (MODE == 2) {
+    if (fl & LIN_F_END) red_add(c.pye + pos, post);
+  }
+}
+// right-hand emissions only: the motif may also end with the sequence
+template <int MODE> RDEV void hook_emit_right(const LinCtx& c, int fl, int pos, double post) {
+  hook_emit<MODE>(c, fl, pos, post);
+  if (MODE == 2 && (fl & LIN_F_ENDL) && pos == c.q.L - 1) red_add(c.pye + c.q.L, post);
+}
 
 // flat offsets (one band table of one sequence has < 2^31 entries: checked by the host)
 RDEV unsigned cidx(const SeqView& q, int row, int d) { return (unsigned)((row * q.W1 + d) * q.S); }
@@ -665,6 +685,7 @@ RDEV void lin_in_L(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
   double* part = w.partA;
   const int xr = q.x[j - 1];
   const double wsr = c.wsf[j - 1];
+  const bool atR = (j - 1 == c.ys);
   const double* src = t.aLl + cidx(q, i, d - 1);
   for (int a = lane; a < h.n_right; a += WARP_N) {
     int fl = ld_ro(h.r_flag + a);
@@ -672,6 +693,7 @@ RDEV void lin_in_L(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
     if (fl & 2) {
       v = src[ld_ro(h.r_src + a)] * ld_ro(p.r_w + a * 5 + xr);
       if (fl & 1) v *= wsr;
+      if (atR && !(fl & LIN_F_START)) v = 0.;
     }
     part[a] = v;
   }
@@ -711,6 +733,7 @@ RDEV void lin_in_P(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w) {
       double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr);
       if (fl & 1) wt *= wsl;
       if (fl & 2) wt *= wsr;
+      if ((i == c.ys && !(fl & LIN_F_START)) || (j - 1 == c.ys && !(fl & LIN_F_RSTART))) wt = 0.;
       if (cE) v += srcE[s1] * wt;
       if (cPP) v += srcP[s1] * wt * (ld_ro(h.slot + ld_ro(h.p_tgt + a)) ? f1 : f0);
     }
@@ -771,8 +794,10 @@ RDEV void lin_in_B(const LinCtx& c, const CTabs& t, int i, int d, bool gP, bool 
     for (int a = lane; a < h.n_right; a += WARP_N) {
       double v = 0.;
       if (ok2) {
+        int fl = ld_ro(h.r_flag + a);
         v = src2[ld_ro(h.r_src + a)] * ld_ro(p.r_w + a * 5 + xr);
-        if (ld_ro(h.r_flag + a) & 1) v *= wsr;
+        if (fl & 1) v *= wsr;
+        if (j - 1 == c.ys && !(fl & LIN_F_START)) v = 0.;
       }
       part[a] = v;
     }
@@ -800,8 +825,10 @@ RDEV void lin_in_B(const LinCtx& c, const CTabs& t, int i, int d, bool gP, bool 
     for (int a = lane; a < h.n_left; a += WARP_N) {
       double v = 0.;
       if (okM) {
+        int fl = ld_ro(h.l_flag + a);
         v = srcM[ld_ro(h.l_src + a)] * ld_ro(p.l_w + a * 5 + xl);
-        if (ld_ro(h.l_flag + a) & 1) v *= wsl;
+        if (fl & 1) v *= wsl;
+        if (i == c.ys && !(fl & LIN_F_START)) v = 0.;
       }
       part[a] = v;
     }
@@ -924,8 +951,10 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
     const int xr = q.x[j - 1];
     const double wsr = c.wsf[j - 1];
     for (int a = lane; a < h.n_right; a += WARP_N) {
+      int fl = ld_ro(h.r_flag + a);
       double v = t.aO[(unsigned)(j - 1) * S + ld_ro(h.r_src + a)] * ld_ro(p.r_w + a * 5 + xr);
-      if (ld_ro(h.r_flag + a) & 1) v *= wsr;
+      if (fl & 1) v *= wsr;
+      if (j - 1 == c.ys && !(fl & LIN_F_START)) v = 0.;
       part[a] = v;
     }
     w_sync();
@@ -945,7 +974,7 @@ template <int NCH> struct EhAcc {
 };
 
 // exterior row top-down, one warp.  bO(L,.) must hold the root weights.
-template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
+template <int NCH, int MODE = 0> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
   const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
@@ -989,14 +1018,16 @@ template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, Wa
     const double wsr = c.wsf[i];
     for (int pz = lane; pz < h.n_right; pz += WARP_N) {
       int a = ld_ro(h.rT_ord + pz);
-      int sp = ld_ro(h.r_tgt + a), ch_s = ld_ro(h.r_src + a);
+      int sp = ld_ro(h.r_tgt + a), ch_s = ld_ro(h.r_src + a), fl = ld_ro(h.r_flag + a);
       double wt = ld_ro(p.r_w + a * 5 + xr);
-      if (ld_ro(h.r_flag + a) & 1) wt *= wsr;
+      if (fl & 1) wt *= wsr;
+      if (i == c.ys && !(fl & LIN_F_START)) wt = 0.;
       double ac = t.aO[(unsigned)i * S + ch_s];
       for (int ch = 0; ch < NCH; ++ch) {
         double contrib = t.bO[ch * t.boch + (unsigned)(i + 1) * S + sp] * wt;
         w.partA[ch * NM + pz] = contrib;
-        if (!p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
+        if (MODE != 2 && !p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
+        if (MODE != 0 && ch == 0 && contrib != 0.) hook_emit_right<MODE>(c, fl, i, contrib * ac);
       }
     }
     w_sync();
@@ -1009,7 +1040,7 @@ template <int NCH> RDEV void lin_outside_ext(const LinCtx& c, const CTabs& t, Wa
 
 // ---- outside, phase EM: E(i,j,s1) <- parent P(i-1,j+1,s) (pair emission at i-1 and j);
 //                         M(i,j,s)  <- E(i,j,s) | parent M(i-1,j,sp) emitting x[i-1]
-template <int NCH>
+template <int NCH, int MODE = 0>
 RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, bool gM, WarpLin& w, EhAcc<NCH>& eh) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
@@ -1028,12 +1059,17 @@ RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, boo
       double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr);
       if (fl & 1) wt *= wsl;
       if (fl & 2) wt *= wsr;
+      if ((i - 1 == c.ys && !(fl & LIN_F_START)) || (j == c.ys && !(fl & LIN_F_RSTART))) wt = 0.;
       double ac = t.aE[il + s1];
       for (int ch = 0; ch < NCH; ++ch) {
         double contrib = t.bP[ch * t.bch + pb + s] * wt;
         w.partA[ch * NM + pz] = contrib;
         double post = contrib * ac;
-        if (!p.no_prf && post != 0.) red_add(w.pcnt + ch * w.pstride + a * 25 + xl * 5 + xr, post);
+        if (MODE != 2 && !p.no_prf && post != 0.) red_add(w.pcnt + ch * w.pstride + a * 25 + xl * 5 + xr, post);
+        if (MODE != 0 && ch == 0 && post != 0.) {
+          hook_emit<MODE>(c, fl, i - 1, post);
+          hook_emit_right<MODE>(c, fl >> 4, j, post);
+        }
       }
     }
     w_sync();
@@ -1062,13 +1098,16 @@ RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, boo
       for (int pz = lane; pz < h.n_left; pz += WARP_N) {
         int a = ld_ro(h.lT_ord + pz);
         int sp = ld_ro(h.l_tgt + a), s1 = ld_ro(h.l_src + a);
+        int fl = ld_ro(h.l_flag + a);
         double wt = ld_ro(p.l_w + a * 5 + xl);
-        if (ld_ro(h.l_flag + a) & 1) wt *= wsl;
+        if (fl & 1) wt *= wsl;
+        if (i - 1 == c.ys && !(fl & LIN_F_START)) wt = 0.;
         double ac = t.aM[il + s1];
         for (int ch = 0; ch < NCH; ++ch) {
           double contrib = t.bM[ch * t.bch + pb + sp] * wt;
           w.partA[ch * NM + pz] = contrib;
-          if (!p.no_prf) w.cntL[(ch * h.n_left + a) * 5 + xl] += contrib * ac;
+          if (MODE != 2 && !p.no_prf) w.cntL[(ch * h.n_left + a) * 5 + xl] += contrib * ac;
+          if (MODE != 0 && ch == 0 && contrib != 0.) hook_emit<MODE>(c, fl, i - 1, contrib * ac);
         }
       }
       w_sync();
@@ -1093,7 +1132,7 @@ RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, boo
 // ---- outside, phase B (cells with gB):
 //   1(i,j,sl): left child of B(i,j',s) with right sibling 2(j,j',sr);   B = 1 + M
 //   2(i,j,sr): right child of B(i',j,s) with left sibling 1(i',i,sl); + 1(i,j,sr); + parent 2(i,j+1,sp) emitting x[j]
-template <int NCH> RDEV void lin_out_B(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpLin& w) {
+template <int NCH, int MODE = 0> RDEV void lin_out_B(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpLin& w) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
   const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
@@ -1199,14 +1238,16 @@ template <int NCH> RDEV void lin_out_B(const LinCtx& c, const CTabs& t, int i, i
       const unsigned pb = cidx(q, i, d + 1);
       for (int pz = lane; pz < h.n_right; pz += WARP_N) {
         int a = ld_ro(h.rT_ord + pz);
-        int sp = ld_ro(h.r_tgt + a), s1 = ld_ro(h.r_src + a);
+        int sp = ld_ro(h.r_tgt + a), s1 = ld_ro(h.r_src + a), fl = ld_ro(h.r_flag + a);
         double wt = ld_ro(p.r_w + a * 5 + xr);
-        if (ld_ro(h.r_flag + a) & 1) wt *= wsr;
+        if (fl & 1) wt *= wsr;
+        if (j == c.ys && !(fl & LIN_F_START)) wt = 0.;
         double ac = t.a2[ir + s1];
         for (int ch = 0; ch < NCH; ++ch) {
           double contrib = t.b2[ch * t.bch + pb + sp] * wt;
           w.partA[ch * NM + pz] = contrib;
-          if (!p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
+          if (MODE != 2 && !p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
+          if (MODE != 0 && ch == 0 && contrib != 0.) hook_emit_right<MODE>(c, fl, j, contrib * ac);
         }
       }
       w_sync();
@@ -1222,7 +1263,7 @@ template <int NCH> RDEV void lin_out_B(const LinCtx& c, const CTabs& t, int i, i
 }
 
 // ---- outside, phase P (cells with an allowed pair)
-template <int NCH>
+template <int NCH, int MODE = 0>
 RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, WarpLin& w, EhAcc<NCH>& eh) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
@@ -1274,13 +1315,18 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
         double wt = ld_ro(p.p_w + a * 25 + xl * 5 + xr) * (sl ? f1 : f0);
         if (fl & 1) wt *= wsl;
         if (fl & 2) wt *= wsr;
+        if ((i - 1 == c.ys && !(fl & LIN_F_START)) || (j == c.ys && !(fl & LIN_F_RSTART))) wt = 0.;
         double ac = t.aP[ir + s1];
         for (int ch = 0; ch < NCH; ++ch) {
           double contrib = t.bP[ch * t.bch + pb + s] * wt;
           w.partA[ch * NM + pz] = contrib;
           double post = contrib * ac;
           eh.add(ch, sl, tsc * post);
-          if (!p.no_prf && post != 0.) red_add(w.pcnt + ch * w.pstride + a * 25 + xl * 5 + xr, post);
+          if (MODE != 2 && !p.no_prf && post != 0.) red_add(w.pcnt + ch * w.pstride + a * 25 + xl * 5 + xr, post);
+          if (MODE != 0 && ch == 0 && post != 0.) {
+            hook_emit<MODE>(c, fl, i - 1, post);
+            hook_emit_right<MODE>(c, fl >> 4, j, post);
+          }
         }
       }
       w_sync();
@@ -1359,7 +1405,7 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
 }
 
 // ---- outside, phase L (every cell): hairpin E(i,j,s) <- L(i,j,s); parent L(i,j+1,sp) emitting x[j]; unpaired flanks
-template <int NCH>
+template <int NCH, int MODE = 0>
 RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, WarpLin& w, EhAcc<NCH>& eh) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
@@ -1403,12 +1449,14 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
       if (fl & 2) {
         wt = ld_ro(p.r_w + a * 5 + xr);
         if (fl & 1) wt *= wsr;
+        if (j == c.ys && !(fl & LIN_F_START)) wt = 0.;
       }
       double ac = t.aLl[il + s1];
       for (int ch = 0; ch < NCH; ++ch) {
         double contrib = (fl & 2) ? t.bL[ch * t.bch + pb + sp] * wt : 0.;
         w.partA[ch * NM + pz] = contrib;
-        if (!p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
+        if (MODE != 2 && !p.no_prf) w.cntR[(ch * h.n_right + a) * 5 + xr] += contrib * ac;
+        if (MODE != 0 && ch == 0 && contrib != 0.) hook_emit_right<MODE>(c, fl, j, contrib * ac);
       }
     }
     w_sync();

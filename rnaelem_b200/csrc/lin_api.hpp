@@ -33,6 +33,35 @@ struct LinLaunch {
 // returns 0 on success; on failure err holds the message.  launches = kernels launched.
 int lin_estep_launch(LinState*, const LinLaunch&, float* kernel_ms, int* launches, std::string& err);
 
+
+// ---- scanner (RNAelemScanDP::calc_motif_positions, motif_scanner.hpp:186-214) on the linear-space kernels:
+// unconstrained inside/outside (start / inner posteriors, E[N], Ys) and start-constrained inside/outside (end
+// posteriors, Ye).  After the kernels of a chunk are enqueued `after_chunk` is called so that the caller can enqueue
+// the (bit-exact, log-space) Viterbi kernel for the same sequences on the same stream while the chunk's masks are
+// still in the slots.
+struct LinChunkView {
+  int base, count;
+  const double* scratch;
+  unsigned long long stride, masks_off;
+  int mask_words;
+  void* stream;
+};
+typedef int (*lin_chunk_fn)(void* user, const LinChunkView&);
+struct LinScanLaunch {
+  LinHMM h;
+  LinParams p;
+  dp::DevEnergy en, el;
+  double kappa0;
+  dp::BatchView b;
+  int Lmax, max_span;
+  dp::ScanOut so;
+  unsigned char* flag;
+  void* stream;
+  int max_slots;
+};
+int lin_scan_launch(LinState*, const LinScanLaunch&, lin_chunk_fn after_chunk, void* user, float* kernel_ms, int* launches,
+                    std::string& err);
+
 }  // namespace lin
 }  // namespace relem
 #endif

@@ -18,6 +18,13 @@
 namespace relem {
 namespace lin {
 
+// entry flag bits beyond bit 0/1 (see r_flag / l_flag / p_flag below).  Single emissions use START/INNER/END(/ENDL);
+// pair emissions use them for the left base and the R* set for the right base.
+enum {
+  LIN_F_START = 4, LIN_F_INNER = 8, LIN_F_END = 16, LIN_F_ENDL = 32,
+  LIN_F_RSTART = 64, LIN_F_RINNER = 128, LIN_F_REND = 256, LIN_F_RENDL = 512
+};
+
 // device view of the automaton (all int32, one blob)
 struct LinHMM {
   int M, S, n_right, n_left, n_pair, n_split, n_quad, n_max;
@@ -83,11 +90,16 @@ struct LinHost {
     for (int s = 0; s < S; ++s) slot[s] = f.st_l[s] == f.st_r[s] ? 0 : 1;
     o_slot = put(slot); o_loop = put(f.is_loop);
     // ---- right: parent s emits x[j-1] with node s.r
+    // scanner hooks (RNAelemScanDP::OutsideFun / OutsideEndFun, motif_scanner.hpp:420-800): which emissions mark the
+    // motif start / an inner motif position / the motif end, by the parent's and child's interval ends
     std::vector<int> rflag(n_right), ren(n_right * 5, -1);
     for (int a = 0; a < n_right; ++a) {
       int s = f.right_tgt[a];
       int hn = f.st_r[s], c = f.node[hn];
-      rflag[a] = (weighted(c) ? 1 : 0) | (f.is_loop[s] ? 2 : 0);
+      int spr = f.st_r[s], scr = f.st_r[f.right_idx[a]];
+      rflag[a] = (weighted(c) ? 1 : 0) | (f.is_loop[s] ? 2 : 0) | ((scr == 0 && spr == 1) ? LIN_F_START : 0) |
+                 ((spr != 0 && spr != M - 1) ? LIN_F_INNER : 0) | ((scr == M - 2 && spr == M - 1) ? LIN_F_END : 0) |
+                 ((spr == M - 2) ? LIN_F_ENDL : 0);
       int tid = f.theta_id[hn];
       for (int b = 1; b < 5; ++b) if (tid >= 0) ren[a * 5 + b] = f.theta_off[tid] + b - 1;
     }
@@ -97,7 +109,9 @@ struct LinHost {
     for (int a = 0; a < n_left; ++a) {
       int s1 = f.left_idx[a];
       int hn = f.st_l[s1], c = f.node[hn];
-      lflag[a] = weighted(c) ? 1 : 0;
+      int spl = f.st_l[f.left_tgt[a]], scl = f.st_l[s1];
+      lflag[a] = (weighted(c) ? 1 : 0) | ((spl == 0 && scl == 1) ? LIN_F_START : 0) |
+                 ((scl != 0 && scl != M - 1) ? LIN_F_INNER : 0) | ((spl == M - 2 && scl == M - 1) ? LIN_F_END : 0);
       int tid = f.theta_id[hn];
       for (int b = 1; b < 5; ++b) if (tid >= 0) len[a * 5 + b] = f.theta_off[tid] + b - 1;
     }
@@ -109,7 +123,11 @@ struct LinHost {
       int s = f.pair_tgt[a], s1 = f.pair_idx[a];
       int sr = f.st_r[s], s1l = f.st_l[s1];
       int nr = f.node[sr], nl = f.node[s1l];
-      pflag[a] = (weighted(nl) ? 1 : 0) | (weighted(nr) ? 2 : 0);
+      int spl = f.st_l[s], scl = s1l, spr = sr, scr = f.st_r[s1];
+      pflag[a] = (weighted(nl) ? 1 : 0) | (weighted(nr) ? 2 : 0) | ((spl == 0 && scl == 1) ? LIN_F_START : 0) |
+                 ((scl != 0 && scl != M - 1) ? LIN_F_INNER : 0) | ((spl == M - 2 && scl == M - 1) ? LIN_F_END : 0) |
+                 ((scr == 0 && spr == 1) ? LIN_F_RSTART : 0) | ((spr != 0 && spr != M - 1) ? LIN_F_RINNER : 0) |
+                 ((scr == M - 2 && spr == M - 1) ? LIN_F_REND : 0) | ((spr == M - 2) ? LIN_F_RENDL : 0);
       for (int xi = 0; xi < 5; ++xi)
         for (int xj = 0; xj < 5; ++xj) {
           int k = a * 25 + xi * 5 + xj;

@@ -830,15 +830,79 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
   ModelView nullm, m;
   model_views(c, nullm, m);
   BatchView bv = batch_view(b);
-  {
+  // Posterior passes on the linear-space kernels, Viterbi (bit-exact) on the log-space kernel; sequences that leave
+  // the fp64 range there (flag) and RELEM_PATH=log go through the all-in-one log-space scan kernel.
+  const char* path_env = std::getenv("RELEM_PATH");
+  bool use_lin = c->have_lin && !(path_env && std::strcmp(path_env, "log") == 0);
+  int n_fallback = nseq;
+  if (use_lin) {
+    if (!c->lin) c->lin = lin::lin_state_create();
+    if (!c->d_flag.reserve(nseq) || !Dev::zero(c->d_flag.p, nseq)) return fail(c, RELEM_ENOMEM, "flag allocation failed");
+    lin::LinScanLaunch ll;
+    ll.h = c->dlh; ll.p = c->dlp; ll.en = c->den; ll.el = c->denl;
+    ll.kappa0 = std::exp(-0.3);
+    ll.b = bv; ll.Lmax = b->Lmax; ll.max_span = c->max_span; ll.so = so;
+    ll.flag = c->d_flag.as<unsigned char>();
+    ll.max_slots = 0;
+    if (const char* e = std::getenv("RELEM_MAX_SLOTS")) ll.max_slots = std::max(1, std::atoi(e));
+#ifndef RELEM_HOST_EMU
+    ll.stream = (void*)c->stream;
+    CUDA_TRY(c, cudaFuncSetAttribute((const void*)relem_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     L.lay.sm_total));
+#else
+    ll.stream = nullptr;
+#endif
+    struct VitCtx { relem_ctx* c; ModelView m; BatchView bv; Launch* L; ScanOut so; } vc{c, m, bv, &L, so};
+    auto after_chunk = [](void* user, const lin::LinChunkView& cv) -> int {
+      VitCtx& v = *(VitCtx*)user;
+      ExtMasks em;
+      em.scratch = cv.scratch; em.stride = cv.stride; em.masks_off = cv.masks_off; em.mask_words = cv.mask_words;
+      em.base = cv.base; em.count = cv.count;
+      relem_ctx* c = v.c;
+#ifdef RELEM_HOST_EMU
+      *c->d_queue.as<int>() = 0;
+      std::vector<unsigned char> smem(v.L->lay.sm_total + 64);
+      relem_viterbi_kernel(v.m, v.bv, v.L->lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), c->d_n2s.as<int>(), v.so,
+                           em, c->d_flag.as<unsigned char>(), smem.data());
+      return 0;
+#else
+      cudaStream_t st = (cudaStream_t)cv.stream;
+      if (cudaMemsetAsync(c->d_queue.p, 0, sizeof(int), st) != cudaSuccess) return 1;
+      relem_viterbi_kernel<<<std::min(v.L->nslots, cv.count), RELEM_CTA_THREADS, v.L->lay.sm_total, st>>>(
+          v.m, v.bv, v.L->lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), c->d_n2s.as<int>(), v.so, em,
+          c->d_flag.as<unsigned char>());
+      return cudaGetLastError() == cudaSuccess ? 0 : 1;
+#endif
+    };
+    float ms = 0.f; int nl = 0; std::string lerr;
+    int lrc = lin::lin_scan_launch(c->lin, ll, after_chunk, &vc, &ms, &nl, lerr);
+    if (lrc == 1) {
+      use_lin = false;
+    } else {
+      if (lrc) return fail(c, lrc == 3 ? RELEM_ENOMEM : RELEM_ECUDA, "linear-space scan: " + lerr);
+      c->timing.push_back(TimingEntry{"relem_scan_lin_kernels", ms, nl});
+      std::vector<unsigned char> flags(nseq);
+      if (!Dev::d2h(flags.data(), c->d_flag.p, nseq)) return fail(c, RELEM_ECUDA, "flag copy failed");
+      std::vector<int> redo;
+      for (int k = 0; k < nseq; ++k) if (flags[k]) redo.push_back(k);
+      n_fallback = (int)redo.size();
+      if (n_fallback) {
+        if (!upload(c->d_order2, redo)) return fail(c, RELEM_ENOMEM, "fallback list upload failed");
+        bv.order = c->d_order2.as<int>();
+        bv.nseq = n_fallback;
+      }
+    }
+  }
+  if (n_fallback > 0) {
+    if (!Dev::zero(c->d_queue.p, sizeof(int))) return fail(c, RELEM_ECUDA, "queue reset failed");
     Timer t(c, "relem_scan_kernel");
 #ifdef RELEM_HOST_EMU
     std::vector<unsigned char> smem(L.lay.sm_total + 64);
     relem_scan_kernel(nullm, m, bv, L.lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), c->d_n2s.as<int>(), so,
                       smem.data());
 #else
-    relem_scan_kernel<<<L.nslots, RELEM_CTA_THREADS, L.lay.sm_total, c->stream>>>(nullm, m, bv, L.lay, c->d_scratch.as<double>(),
-                                                                     c->d_queue.as<int>(), c->d_n2s.as<int>(), so);
+    relem_scan_kernel<<<std::min(L.nslots, n_fallback), RELEM_CTA_THREADS, L.lay.sm_total, c->stream>>>(
+        nullm, m, bv, L.lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), c->d_n2s.as<int>(), so);
     CUDA_TRY(c, cudaGetLastError());
 #endif
     t.stop();

@@ -44,11 +44,12 @@ struct LinLayout {
   unsigned long long bP, bEl, bEr, bM, bBl, bBr, b2, bL, bO, bch, boch;
   unsigned long long kP, kE, kM, k1, k2, kO, kbP, kbE, kbM, kbBl, kbBr, kb2, kbO, kPm, kbEm;
   // per-slot header
-  unsigned long long hdr;    // [16]: Z^tt, Z^tf, Z^ft, bad, canonical pair count, -, -, -, EH[nch*2]
+  unsigned long long hdr;    // [16]: Z^tt, Z^tf, Z^ft, bad, canonical pair count, L, ys, -, EH[nch*2]
   unsigned long long wsf;    // [Lmax+1] exp(position weight)
   unsigned long long cnt;    // [nch][ncnt] emission posterior sums per (list entry, base)
   unsigned long long masks;  // 4 x (Lmax+2)*mw words: bp, lf, bpr, lfr
   unsigned long long bytes;  // x [Lmax+2], sp3, sp4, sp6 [Lmax+1 each]
+  unsigned long long post;   // scanner: linear start / inner / end posteriors, [Lmax+2] each
   int Lmax, Wmax, mw, nch, ncnt, mask_words;
   int sm_ctx, sm_misc, sm_pcnt, sm_warp, warp_bytes_in, warp_bytes_out;
 };
@@ -80,6 +81,7 @@ static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int nc
   lay.cnt = take((unsigned long long)nch * lay.ncnt);
   lay.masks = take(2ull * lay.mask_words);
   lay.bytes = take((4ull * (Lmax + 2) + 7) / 8);
+  lay.post = take(3ull * (Lmax + 2));
   lay.stride = o;
   int b = 0;
   auto sm = [&](int bytes) { int r = b; b += (bytes + 15) & ~15; return r; };
@@ -102,6 +104,7 @@ struct LinKArgs {
   const double* k0pow;
   int kp_n;          // entries of k0pow before the G table
   EstepOut out;
+  ScanOut so;        // scanner runs only
   unsigned char* flag;
 };
 
@@ -160,6 +163,8 @@ RDEV LinCtx& lin_attach(const LinKArgs& a, unsigned char* smem_raw, int sk, doub
     q.ws = a.b.ws + o; q.emit0 = nullptr; q.emitT = nullptr;
     c.wsf = slot + lay.wsf; c.k0pow = a.k0pow;
     c.Ceff = C < 30 ? C : 30;
+    c.ys = FROM_HDR ? (int)slot[lay.hdr + 6] : -1;
+    c.pys = slot + lay.post; c.pyi = c.pys + (lay.Lmax + 2); c.pye = c.pyi + (lay.Lmax + 2);
   }
   CTA_SYNC();
   return c;
@@ -219,6 +224,7 @@ LIN_KERNEL(LIN_THREADS, 8) relem_lin_prep_kernel(LinKArgs a LIN_SMEM_ARG) {
   if (CTA_TID == 0) { x[L] = 0; x[L + 1] = 0; }
   for (int t = CTA_TID; t < 16; t += CTA_NTH) slot[lay.hdr + t] = 0.;
   for (int t = CTA_TID; t < lay.nch * lay.ncnt; t += CTA_NTH) slot[lay.cnt + t] = 0.;
+  for (int t = CTA_TID; t < 3 * (lay.Lmax + 2); t += CTA_NTH) slot[lay.post + t] = 0.;
   CTA_SYNC();
   cta_special_hairpins(LC.en, x, L, (signed char*)q.sp3, (signed char*)q.sp4, (signed char*)q.sp6);
   unsigned* mk = (unsigned*)(slot + lay.masks);
@@ -233,7 +239,8 @@ LIN_KERNEL(LIN_THREADS, 8) relem_lin_prep_kernel(LinKArgs a LIN_SMEM_ARG) {
   if (CTA_TID == 0) {
     slot[lay.hdr + 4] = (double)total;
     slot[lay.hdr + 5] = (double)L;
-    a.out.bpp_eff[n] = 1.;
+    slot[lay.hdr + 6] = -1.;
+    if (a.out.bpp_eff) a.out.bpp_eff[n] = 1.;
   }
 }
 
@@ -266,7 +273,7 @@ template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot
 
 // grid = count * ntile CTAs; CTA (sk, tk) owns cells [tk*tile, (tk+1)*tile) of diagonal d of sequence slot sk,
 // its warps take them interleaved
-template <int PH, int NCH>
+template <int PH, int NCH, int MODE = 0>
 LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 7)) relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -323,11 +330,11 @@ LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 7)) relem_lin_phase_kernel(LinKAr
     for (int i = i0 + w0; i < i1; i += nw) {
       if (PH == PH_OUT_EM) {
         bool gE = ok_E(q, i, d), gM = ok_M(q, i, d);
-        if (gE || gM) lin_out_EM<NCH>(c, t, i, d, gE, gM, w, eh);
+        if (gE || gM) lin_out_EM<NCH, MODE>(c, t, i, d, gE, gM, w, eh);
       }
-      if (PH == PH_OUT_B) { if (ok_B(q, i, d)) lin_out_B<NCH>(c, t, i, d, ok_M(q, i, d), w); }
-      if (PH == PH_OUT_P) { if (ok_P(q, i, d)) lin_out_P<NCH>(c, t, i, d, ok_B(q, i, d), w, eh); }
-      if (PH == PH_OUT_L) lin_out_L<NCH>(c, t, i, d, d >= 3 && ok_E(q, i, d), w, eh);
+      if (PH == PH_OUT_B) { if (ok_B(q, i, d)) lin_out_B<NCH, MODE>(c, t, i, d, ok_M(q, i, d), w); }
+      if (PH == PH_OUT_P) { if (ok_P(q, i, d)) lin_out_P<NCH, MODE>(c, t, i, d, ok_B(q, i, d), w, eh); }
+      if (PH == PH_OUT_L) lin_out_L<NCH, MODE>(c, t, i, d, d >= 3 && ok_E(q, i, d), w, eh);
     }
     lin_flush_counts<NCH>(lay, slot, w, eh);
   }
@@ -336,7 +343,7 @@ LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 7)) relem_lin_phase_kernel(LinKAr
 // ------------------------------------------------------------------------------------------------ exterior rows
 // one warp per sequence.  WHICH: 0 energy-only inside, 1 energy-only outside, 2 coupled inside (+ partition functions,
 // root weights), 3 coupled outside
-template <int WHICH, int NCH> LIN_KERNEL(32, 16) relem_lin_ext_kernel(LinKArgs a LIN_SMEM_ARG) {
+template <int WHICH, int NCH, int MODE = 0> LIN_KERNEL(32, 16) relem_lin_ext_kernel(LinKArgs a LIN_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
@@ -374,25 +381,25 @@ template <int WHICH, int NCH> LIN_KERNEL(32, 16) relem_lin_ext_kernel(LinKArgs a
     const double rM2 = h.s0M2 >= 0 ? ld_cg(t.aO + (unsigned)L * S + h.s0M2) : 0.;
     const double rM1 = h.s0M1 >= 0 ? ld_cg(t.aO + (unsigned)L * S + h.s0M1) : 0.;
     const double Ztt = r00 + (rM2 + rM1), Ztf = rM2 + rM1, Zft = r00;
-    const int kind = a.b.kind[n];
-    // every partition function the trainer tests must be representable; otherwise the log-space path decides
-    const bool bad = !finite_pos(Ztt) || (kind != 2 && !finite_pos(Ztf)) || !(Zft >= 0. && Zft < (-NINF));
-    if (bad) {
-      if (lane_id() == 0) { slot[lay.hdr + 3] = 1.; a.flag[n] = 1; }
-      return;
-    }
-    if (lane_id() == 0) {
-      slot[lay.hdr + 0] = Ztt; slot[lay.hdr + 1] = Ztf; slot[lay.hdr + 2] = Zft;
-      const double shift = -(double)L * LC.p.ln_kappa;  // ln Z = ln Z^ - L ln kappa
-      a.out.Z[n * 3 + 0] = log(Ztt) + shift;
-      a.out.Z[n * 3 + 1] = Ztf > 0. ? log(Ztf) + shift : NINF;
-      a.out.Z[n * 3 + 2] = Zft > 0. ? log(Zft) + shift : NINF;
-      a.out.skipped[n] = 0;
-    }
-    // root weights of the outside pass: channel 0 = Zo (all three roots), channel 1 = the restricted condition;
-    // NCH = 1 carries their difference
     double rw[NCH][3];
-    {
+    if (MODE == 0) {
+      const int kind = a.b.kind[n];
+      // every partition function the trainer tests must be representable; otherwise the log-space path decides
+      const bool bad = !finite_pos(Ztt) || (kind != 2 && !finite_pos(Ztf)) || !(Zft >= 0. && Zft < (-NINF));
+      if (bad) {
+        if (lane_id() == 0) { slot[lay.hdr + 3] = 1.; a.flag[n] = 1; }
+        return;
+      }
+      if (lane_id() == 0) {
+        slot[lay.hdr + 0] = Ztt; slot[lay.hdr + 1] = Ztf; slot[lay.hdr + 2] = Zft;
+        const double shift = -(double)L * LC.p.ln_kappa;  // ln Z = ln Z^ - L ln kappa
+        a.out.Z[n * 3 + 0] = log(Ztt) + shift;
+        a.out.Z[n * 3 + 1] = Ztf > 0. ? log(Ztf) + shift : NINF;
+        a.out.Z[n * 3 + 2] = Zft > 0. ? log(Zft) + shift : NINF;
+        a.out.skipped[n] = 0;
+      }
+      // root weights of the outside pass: channel 0 = Zo (all three roots), channel 1 = the restricted condition;
+      // NCH = 1 carries their difference
       double o0 = 1. / Ztt;
       double x00 = 0., xM = 0.;
       if (kind == 1) xM = 1. / Ztf;
@@ -403,6 +410,18 @@ template <int WHICH, int NCH> LIN_KERNEL(32, 16) relem_lin_ext_kernel(LinKArgs a
       } else {
         rw[0][0] = o0 - x00; rw[0][1] = o0 - xM; rw[0][2] = o0 - xM;
       }
+    } else if (MODE == 1) {
+      // scanner, unconstrained pass: posteriors relative to Z(1,1) (calc_motif_start_position, motif_scanner.hpp:186-193)
+      if (!finite_pos(Ztt)) {
+        if (lane_id() == 0) { slot[lay.hdr + 3] = 1.; a.flag[n] = 1; }
+        return;
+      }
+      if (lane_id() == 0 && a.so.ZL) a.so.ZL[n] = log(Ztt) - (double)L * LC.p.ln_kappa;
+      for (int k = 0; k < 3; ++k) rw[0][k] = 1. / Ztt;
+    } else {
+      // scanner, start fixed: a sequence in which the motif cannot start anywhere has Z = 0 and no end posterior
+      const double o0 = finite_pos(Ztt) ? 1. / Ztt : 0.;
+      for (int k = 0; k < 3; ++k) rw[0][k] = o0;
     }
     for (int tt = lane_id(); tt < NCH * S; tt += WARP_N) {
       int ch = tt / S, s = tt - ch * S;
@@ -423,7 +442,7 @@ template <int WHICH, int NCH> LIN_KERNEL(32, 16) relem_lin_ext_kernel(LinKArgs a
     w_sync();
     EhAcc<NCH> eh;
     for (int k = 0; k < NCH * 2; ++k) eh.v[k] = 0.;
-    lin_outside_ext<NCH>(c, t, w);
+    lin_outside_ext<NCH, MODE>(c, t, w);
     lin_flush_counts<NCH>(lay, slot, w, eh);
   }
 }
@@ -465,7 +484,7 @@ LIN_KERNEL(LIN_THREADS, 8) relem_lin_filter_kernel(LinKArgs a LIN_SMEM_ARG) {
   cta_right_mask(q, bp, mk + 2 * lay.mask_words);
   CTA_SYNC();
   cta_right_mask(q, lf, mk + 3 * lay.mask_words);
-  if (CTA_TID == 0) a.out.bpp_eff[n] = (double)nbp / slot[lay.hdr + 4];
+  if (CTA_TID == 0 && a.out.bpp_eff) a.out.bpp_eff[n] = (double)nbp / slot[lay.hdr + 4];
 }
 
 // ------------------------------------------------------------------------------------------------ fold
@@ -517,6 +536,85 @@ template <int NCH> LIN_KERNEL(LIN_THREADS, 8) relem_lin_fold_kernel(LinKArgs a L
     a.out.EH[n * 4 + 0] = ehv[0]; a.out.EH[n * 4 + 1] = ehv[1];
     a.out.EH[n * 4 + 2] = NCH == 2 ? ehv[(NCH - 1) * 2] : 0.;
     a.out.EH[n * 4 + 3] = NCH == 2 ? ehv[(NCH - 1) * 2 + 1] : 0.;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ scanner folds
+// index of the last maximum (max_index, util.hpp:231-241); NaN never wins
+RDEV int lin_last_max(const double* v, int n) {
+  int s = 0;
+  double mx = -1.7976931348623157e308;
+  for (int i = 0; i < n; ++i)
+    if (mx <= v[i]) { s = i; mx = v[i]; }
+  return s;
+}
+// STAGE 1 (after the unconstrained pass): E[N], log start / inner posteriors, exist prob, Ys (-> header).
+// STAGE 2 (after the start-constrained pass): log end posteriors, Ye.   One CTA per sequence.
+template <int STAGE> LIN_KERNEL(LIN_THREADS, 8) relem_lin_scanfold_kernel(LinKArgs a LIN_SMEM_ARG) {
+#ifndef RELEM_HOST_EMU
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
+  const LinLayout& lay = a.lay;
+  const LinHMM& h = LC.h;
+  const int NT = LC.p.n_theta;
+  const int sk = LIN_BLOCK_IDX;
+  if (sk >= a.count) return;
+  double* slot = a.scratch + (unsigned long long)sk * lay.stride;
+  if (slot[lay.hdr + 3] != 0.) return;
+  const int n = a.b.order[a.base + sk];
+  const long long o = a.b.off[n];
+  const int L = (int)slot[lay.hdr + 5];
+  double* pys = slot + lay.post; double* pyi = pys + (lay.Lmax + 2); double* pye = pyi + (lay.Lmax + 2);
+  if (STAGE == 1) {
+    double* sen = (double*)smem_raw;  // [NT]
+    for (int tt = CTA_TID; tt < NT; tt += CTA_NTH) sen[tt] = 0.;
+    CTA_SYNC();
+    const double* g = slot + lay.cnt;
+    const int nR = 5 * h.n_right, nL = 5 * h.n_left;
+    for (int r = CTA_TID; r < lay.ncnt; r += CTA_NTH) {
+      double v = ld_cg(g + r);
+      if (v == 0.) continue;
+      if (r < nR) { int idx = ld_ro(h.r_en + r); if (idx >= 0) sm_add(sen + idx, v); }
+      else if (r < nR + nL) { int idx = ld_ro(h.l_en + (r - nR)); if (idx >= 0) sm_add(sen + idx, v); }
+      else {
+        int i1 = ld_ro(h.p_en1 + (r - nR - nL)), i2 = ld_ro(h.p_en2 + (r - nR - nL));
+        if (i1 >= 0) sm_add(sen + i1, v);
+        if (i2 >= 0) sm_add(sen + i2, v);
+      }
+    }
+    CTA_SYNC();
+    bool okv = true;
+    for (int tt = 0; tt < NT; ++tt) okv = okv && (sen[tt] - sen[tt] == 0.);
+    if (!okv) {
+      if (CTA_TID == 0) { slot[lay.hdr + 3] = 1.; a.flag[n] = 1; }
+      return;
+    }
+    for (int tt = CTA_TID; tt < NT; tt += CTA_NTH) a.so.EN[(long long)n * NT + tt] = sen[tt];
+    for (int tt = CTA_TID; tt < L; tt += CTA_NTH) {
+      double s0 = ld_cg(pys + tt), s1 = ld_cg(pyi + tt);
+      double ls = s0 > 0. ? log(s0) : NINF;
+      pys[tt] = ls;
+      a.so.PysL[o + tt] = ls;
+      a.so.PyiL[o + tt] = s1 > 0. ? log(s1) : NINF;
+    }
+    CTA_SYNC();
+    if (CTA_TID == 0) {
+      const int ys = lin_last_max(pys, L);
+      double ex = 0.;  // exp(sumL(PysL)), motif_scanner.hpp:246
+      for (int tt = 0; tt < L; ++tt) if (pys[tt] > NINF) ex += exp(pys[tt]);
+      a.so.exist[n] = ex;
+      a.so.Ys[n] = ys;
+      slot[lay.hdr + 6] = (double)ys;
+    }
+  } else {
+    for (int tt = CTA_TID; tt <= L; tt += CTA_NTH) {
+      double e0 = ld_cg(pye + tt);
+      double le = e0 > 0. ? log(e0) : NINF;
+      pye[tt] = le;
+      a.so.PyeL[o + n + tt] = le;
+    }
+    CTA_SYNC();
+    if (CTA_TID == 0) a.so.Ye[n] = lin_last_max(pye, L + 1);
   }
 }
 
@@ -584,6 +682,14 @@ template <int PH, int NCH> static void launch_phase(Runner& r, int d, int tile, 
   LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, NCH>), r.a.count * r.a.ntile, LIN_THREADS, smem);
 }
 
+template <int PH, int MODE> static void launch_phase3(Runner& r, int d, int tile, int smem) {
+  const int ncell_max = r.a.lay.Lmax + 1 - d;
+  if (ncell_max <= 0) return;
+  if (tile > ncell_max) tile = ncell_max;
+  r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile;
+  LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, 1, MODE>), r.a.count * r.a.ntile, LIN_THREADS, smem);
+}
+
 template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
   const int W = r.a.lay.Wmax, cnt = r.a.count;
   LIN_LAUNCH(r, relem_lin_prep_kernel, cnt, LIN_THREADS, r.smem_small);
@@ -613,6 +719,56 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
     launch_phase<PH_OUT_L, NCH>(r, d, r.tile_d, r.smem_out);
   }
   LIN_LAUNCH(r, (relem_lin_fold_kernel<NCH>), cnt, LIN_THREADS, NCH * NT * 8 + 16);
+}
+
+// scanner: unconstrained inside/outside (start / inner posteriors, E[N]) -> Ys -> start-constrained inside/outside
+// (end posteriors) -> Ye.  The Viterbi pass is launched by the caller afterwards (it must stay bit-exact).
+static void run_chunk_scan(Runner& r, bool filter, int NT) {
+  const int W = r.a.lay.Wmax, cnt = r.a.count;
+  LIN_LAUNCH(r, relem_lin_prep_kernel, cnt, LIN_THREADS, r.smem_small);
+  if (filter) {
+    for (int d = 3; d <= W; ++d) launch_phase<PH_K0_IN, 1>(r, d, r.tile_k0, r.smem_k0);
+    LIN_LAUNCH(r, (relem_lin_ext_kernel<0, 1>), cnt, 32, r.smem_small);
+    LIN_LAUNCH(r, (relem_lin_ext_kernel<1, 1>), cnt, 32, r.smem_small);
+    for (int d = W; d >= 3; --d) launch_phase<PH_K0_OUT, 1>(r, d, r.tile_k0, r.smem_k0);
+    LIN_LAUNCH(r, relem_lin_filter_kernel, cnt, LIN_THREADS, r.smem_small);
+  }
+  for (int pass = 1; pass <= 2; ++pass) {
+    for (int d = 0; d <= W; ++d) {
+      launch_phase<PH_IN_L, 1>(r, d, r.tile_d, r.smem_in);
+      if (d >= 5) {
+        launch_phase<PH_IN_P, 1>(r, d, r.tile_p, r.smem_in);
+        launch_phase<PH_IN_B, 1>(r, d, r.tile_d, r.smem_in);
+      }
+      if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, r.tile_e, r.smem_in);
+    }
+    if (pass == 1) {
+      LIN_LAUNCH(r, (relem_lin_ext_kernel<2, 1, 1>), cnt, 32, r.smem_ext_in);
+      LIN_LAUNCH(r, (relem_lin_ext_kernel<3, 1, 1>), cnt, 32, r.smem_ext_out);
+    } else {
+      LIN_LAUNCH(r, (relem_lin_ext_kernel<2, 1, 2>), cnt, 32, r.smem_ext_in);
+      LIN_LAUNCH(r, (relem_lin_ext_kernel<3, 1, 2>), cnt, 32, r.smem_ext_out);
+    }
+    for (int d = W; d >= 0; --d) {
+      if (pass == 1) {
+        if (d >= 3) launch_phase3<PH_OUT_EM, 1>(r, d, r.tile_p, r.smem_out);
+        if (d >= 5) {
+          launch_phase3<PH_OUT_B, 1>(r, d, r.tile_d, r.smem_out);
+          launch_phase3<PH_OUT_P, 1>(r, d, r.tile_e, r.smem_out);
+        }
+        launch_phase3<PH_OUT_L, 1>(r, d, r.tile_d, r.smem_out);
+      } else {
+        if (d >= 3) launch_phase3<PH_OUT_EM, 2>(r, d, r.tile_p, r.smem_out);
+        if (d >= 5) {
+          launch_phase3<PH_OUT_B, 2>(r, d, r.tile_d, r.smem_out);
+          launch_phase3<PH_OUT_P, 2>(r, d, r.tile_e, r.smem_out);
+        }
+        launch_phase3<PH_OUT_L, 2>(r, d, r.tile_d, r.smem_out);
+      }
+    }
+    if (pass == 1) LIN_LAUNCH(r, (relem_lin_scanfold_kernel<1>), cnt, LIN_THREADS, NT * 8 + 16);
+    else LIN_LAUNCH(r, (relem_lin_scanfold_kernel<2>), cnt, LIN_THREADS, 16);
+  }
 }
 
 int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* launches, std::string& err) {
@@ -727,6 +883,108 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
     }
   }
   r.stream = main_stream;
+  e = cudaGetLastError();
+  cudaEventRecord(e1, r.stream);
+  if (e != cudaSuccess) { err = std::string("linear-space kernel launch: ") + cudaGetErrorString(e); return 2; }
+  e = cudaEventSynchronize(e1);
+  if (e != cudaSuccess) { err = std::string("linear-space kernels: ") + cudaGetErrorString(e); return 2; }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (kernel_ms) *kernel_ms = ms;
+  if (launches) *launches = r.launches;
+  return 0;
+#endif
+}
+
+int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_chunk, void* user, float* kernel_ms,
+                    int* launches, std::string& err) {
+  if (kernel_ms) *kernel_ms = 0.f;
+  if (launches) *launches = 0;
+  LinConst hc;
+  hc.h = in.h; hc.p = in.p; hc.en = in.en; hc.el = in.el; hc.k0 = in.kappa0; hc.k0sq = in.kappa0 * in.kappa0;
+  Runner r;
+  LinKArgs& a = r.a;
+  std::memset(&a.out, 0, sizeof(a.out));
+  a.b = in.b; a.so = in.so; a.flag = in.flag;
+  const int nseq = in.b.nseq;
+  a.lay = make_lin_layout(std::max(1, in.Lmax), in.max_span, in.h, 1);
+  const LinLayout& lay = a.lay;
+  r.smem_small = lay.sm_warp;
+  r.smem_k0 = lay.sm_warp + LIN_WARPS * 128 * 4;
+  r.smem_in = lay.sm_warp + LIN_WARPS * lay.warp_bytes_in;
+  r.smem_out = lay.sm_warp + LIN_WARPS * lay.warp_bytes_out;
+  r.smem_ext_in = lay.sm_warp + lay.warp_bytes_in;
+  r.smem_ext_out = lay.sm_warp + lay.warp_bytes_out;
+  const int NT = in.p.n_theta;
+  const int KP = std::max(256, (lay.Wmax + 3 + 31) & ~31);
+  std::vector<double> kp(KP + 1024, 0.);
+  for (int t = 0; t < KP; ++t) kp[t] = std::pow(in.kappa0, (double)t);
+  size_t per = (size_t)lay.stride * sizeof(double);
+  LinChunkView cv;
+  cv.stride = lay.stride; cv.masks_off = lay.masks; cv.mask_words = lay.mask_words;
+#ifdef RELEM_HOST_EMU
+  LC = hc;
+  if (per > st->scratch_bytes) {
+    std::free(st->scratch);
+    st->scratch = std::malloc(per);
+    st->scratch_bytes = st->scratch ? per : 0;
+  }
+  if (!st->scratch) { err = "scratch allocation failed"; return 3; }
+  std::free(st->k0pow);
+  st->k0pow = std::malloc(kp.size() * 8);
+  std::memcpy(st->k0pow, kp.data(), kp.size() * 8);
+  a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
+  r.smem.assign(std::max(std::max(r.smem_out, r.smem_in), NT * 8 + 16) + 64, 0);
+  LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
+  for (int k = 0; k < nseq; ++k) {
+    { double* p = (double*)st->scratch; for (size_t z = 0; z < per / 8; ++z) p[z] = std::nan(""); }
+    a.base = k; a.count = 1;
+    run_chunk_scan(r, in.en.filter != 0, NT);
+    cv.base = k; cv.count = 1; cv.scratch = a.scratch; cv.stream = nullptr;
+    if (after_chunk && after_chunk(user, cv)) { err = "Viterbi launch failed"; return 2; }
+  }
+  if (launches) *launches = r.launches;
+  return 0;
+#else
+  if (r.smem_out > 227 * 1024) { err = "pattern too large for the linear-space kernel's shared memory"; return 1; }
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  long long by_mem = (long long)(((double)(free_b + st->scratch_bytes) * 0.70) / (double)per);
+  if (in.max_slots > 0) by_mem = std::min<long long>(by_mem, in.max_slots);
+  if (by_mem < 1) { err = "not enough device memory for one sequence slot"; return 3; }
+  long long nslots = std::min<long long>(nseq, by_mem);
+  const long long have = (long long)(st->scratch_bytes / per);
+  if (have >= 1 && have < nslots && have * 10 >= nslots * 8) nslots = have;
+  size_t need = (size_t)nslots * per;
+  if (need > st->scratch_bytes) {
+    if (st->scratch) cudaFree(st->scratch);
+    st->scratch = nullptr; st->scratch_bytes = 0;
+    if (cudaMalloc(&st->scratch, need) != cudaSuccess) { err = "scratch allocation failed"; return 3; }
+    st->scratch_bytes = need;
+  }
+  if (st->k0pow_n < kp.size()) {
+    if (st->k0pow) cudaFree(st->k0pow);
+    st->k0pow = nullptr; st->k0pow_n = 0;
+    if (cudaMalloc(&st->k0pow, kp.size() * 8) != cudaSuccess) { err = "allocation failed"; return 3; }
+    st->k0pow_n = kp.size();
+  }
+  r.stream = (cudaStream_t)in.stream;
+  cudaError_t e = cudaMemcpyAsync(st->k0pow, kp.data(), kp.size() * 8, cudaMemcpyHostToDevice, r.stream);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(LC, &hc, sizeof(LinConst), 0, cudaMemcpyHostToDevice, r.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(r.stream);
+  if (e != cudaSuccess) { err = std::string("constant upload: ") + cudaGetErrorString(e); return 2; }
+  a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, r.stream);
+  LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
+  for (int base = 0; base < nseq; base += (int)nslots) {
+    a.base = base; a.count = std::min<int>((int)nslots, nseq - base);
+    run_chunk_scan(r, in.en.filter != 0, NT);
+    cv.base = a.base; cv.count = a.count; cv.scratch = a.scratch; cv.stream = (void*)r.stream;
+    if (after_chunk && after_chunk(user, cv)) { err = "Viterbi launch failed"; return 2; }
+  }
   e = cudaGetLastError();
   cudaEventRecord(e1, r.stream);
   if (e != cudaSuccess) { err = std::string("linear-space kernel launch: ") + cudaGetErrorString(e); return 2; }
