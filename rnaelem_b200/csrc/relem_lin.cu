@@ -624,7 +624,10 @@ struct LinState {
   size_t scratch_bytes = 0;
   void* k0pow = nullptr;
   size_t k0pow_n = 0;
+  double k0pow_kappa = 0.;   // what the device copy of the kappa0 powers was built for
+  int k0pow_kp = 0;
 #ifndef RELEM_HOST_EMU
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t lane[4] = {nullptr, nullptr, nullptr, nullptr};  // two chunks in flight: one fills the SMs while the other's kernel drains
   cudaEvent_t lane_done[4] = {nullptr, nullptr, nullptr, nullptr};
 #endif
@@ -638,6 +641,8 @@ void lin_state_destroy(LinState* s) {
 #else
   if (s->scratch) cudaFree(s->scratch);
   if (s->k0pow) cudaFree(s->k0pow);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
   for (int k = 0; k < 4; ++k) {
     if (s->lane[k]) cudaStreamDestroy(s->lane[k]);
     if (s->lane_done[k]) cudaEventDestroy(s->lane_done[k]);
@@ -651,6 +656,8 @@ struct Runner {
   LinKArgs a;
   int smem_in, smem_out, smem_small, smem_k0, smem_ext_in, smem_ext_out;
   int launches = 0;
+  int resident_ctas = 148 * 7;
+  int fill = 4;                    // CTAs per resident slot a small launch aims for (RELEM_FILL)
   int tile_p = 128, tile_e = 256;   // cells per CTA of the phases that touch few cells
   int tile_k0 = 32, tile_d = 64;   // cells per CTA of the dense phases (measured sweet spot, RELEM_TILE_*)
 #ifdef RELEM_HOST_EMU
@@ -674,10 +681,21 @@ struct Runner {
   } while (0)
 #endif
 
+// Small chunks (a training minibatch is ~128 sequences) cannot fill the GPU with 64-cell tiles: shrink the tile until
+// the launch has ~2 CTAs per resident slot, down to one cell per warp.
+static int fit_tile(const Runner& r, int tile, int ncell_max) {
+  const long long want = (long long)r.fill * r.resident_ctas;
+  long long t = ((long long)r.a.count * ncell_max + want - 1) / want;   // cells per CTA that give `want` CTAs
+  t = (t + LIN_WARPS - 1) / LIN_WARPS * LIN_WARPS;
+  if (t < LIN_WARPS) t = LIN_WARPS;
+  return (int)std::min<long long>(tile, t);
+}
+
 template <int PH, int NCH> static void launch_phase(Runner& r, int d, int tile, int smem) {
   const int ncell_max = r.a.lay.Lmax + 1 - d;
   if (ncell_max <= 0) return;
   if (tile > ncell_max) tile = ncell_max;
+  tile = fit_tile(r, tile, ncell_max);
   r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile;
   LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, NCH>), r.a.count * r.a.ntile, LIN_THREADS, smem);
 }
@@ -686,6 +704,7 @@ template <int PH, int MODE> static void launch_phase3(Runner& r, int d, int tile
   const int ncell_max = r.a.lay.Lmax + 1 - d;
   if (ncell_max <= 0) return;
   if (tile > ncell_max) tile = ncell_max;
+  tile = fit_tile(r, tile, ncell_max);
   r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile;
   LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, 1, MODE>), r.a.count * r.a.ntile, LIN_THREADS, smem);
 }
@@ -789,6 +808,7 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   r.smem_ext_in = lay.sm_warp + lay.warp_bytes_in;
   r.smem_ext_out = lay.sm_warp + lay.warp_bytes_out;
   const int NT = in.p.n_theta;
+  if (const char* e = std::getenv("RELEM_FILL")) r.fill = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("RELEM_TILE_K0")) r.tile_k0 = std::max(4, std::atoi(e));
   if (const char* e = std::getenv("RELEM_TILE_D")) r.tile_d = std::max(4, std::atoi(e));
   if (const char* e = std::getenv("RELEM_TILE_P")) r.tile_p = std::max(4, std::atoi(e));
@@ -823,9 +843,14 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   return 0;
 #else
   if (r.smem_out > 227 * 1024) { err = "pattern too large for the linear-space kernel's shared memory"; return 1; }
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
-  long long by_mem = (long long)(((double)(free_b + st->scratch_bytes) * 0.70) / (double)per);
+  // a scratch buffer that already holds the whole batch needs no new sizing (cudaMemGetInfo costs milliseconds,
+  // which matters for a training minibatch of ~128 sequences)
+  long long by_mem = (long long)(st->scratch_bytes / per);
+  if (by_mem < nseq) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    by_mem = (long long)(((double)(free_b + st->scratch_bytes) * 0.70) / (double)per);
+  }
   if (in.max_slots > 0) by_mem = std::min<long long>(by_mem, in.max_slots);
   if (by_mem < 1) { err = "not enough device memory for one sequence slot"; return 3; }
   // two lanes (streams) with half of the slots each once there is enough work to keep both busy
@@ -850,15 +875,19 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
     st->k0pow_n = kp.size();
   }
   r.stream = (cudaStream_t)in.stream;
-  cudaError_t e = cudaMemcpyAsync(st->k0pow, kp.data(), kp.size() * 8, cudaMemcpyHostToDevice, r.stream);
+  cudaError_t e = cudaSuccess;
+  const bool new_kp = st->k0pow_kappa != in.kappa0 || st->k0pow_kp != KP;
+  if (new_kp) e = cudaMemcpyAsync(st->k0pow, kp.data(), kp.size() * 8, cudaMemcpyHostToDevice, r.stream);
   if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(LC, &hc, sizeof(LinConst), 0, cudaMemcpyHostToDevice, r.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(r.stream);  // kp / hc are stack objects
   if (e != cudaSuccess) { err = std::string("constant upload: ") + cudaGetErrorString(e); return 2; }
   a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
   cudaStream_t main_stream = r.stream;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  if (!st->ev0) { cudaEventCreate(&st->ev0); cudaEventCreate(&st->ev1); }
+  cudaEvent_t e0 = st->ev0, e1 = st->ev1;
+  // the G table depends on the energy tables and kappa0 only; energy parameters change rarely but cheaply: refill
   LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
+  st->k0pow_kappa = in.kappa0; st->k0pow_kp = KP;
   cudaEventRecord(e0, main_stream);
   if (nlanes >= 2) {
     for (int k = 0; k < nlanes; ++k) {
@@ -890,7 +919,6 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   if (e != cudaSuccess) { err = std::string("linear-space kernels: ") + cudaGetErrorString(e); return 2; }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (kernel_ms) *kernel_ms = ms;
   if (launches) *launches = r.launches;
   return 0;
