@@ -186,6 +186,25 @@ LIN_NOINLINE F2 boltz2(double tsc) {
   return r;
 }
 
+// Exterior rows run over the whole sequence, so a fixed per-base scale cannot keep them inside the fp64 range for long
+// sequences.  They are stored as mantissas with one integer (power-of-two) exponent per position; a column is
+// rescaled whenever its largest entry leaves [2^-256, 2^256].  Band tables need none of this: their span is <= W.
+#ifndef LIN_RENORM_HI   // (tests/test_emu_parity.py also builds the emulation with tiny thresholds to exercise the rescaling)
+#define LIN_RENORM_HI 1.157920892373162e77    // 2^256
+#define LIN_RENORM_LO 8.636168555094445e-78   // 2^-256
+#endif
+RDEV int renorm_shift(double m) {  // m = largest magnitude of the column
+  return (m > LIN_RENORM_HI || (m > 0. && m < LIN_RENORM_LO)) ? (int)ilogb(m) : 0;
+}
+#ifdef RELEM_HOST_EMU
+RDEV double w_max(double v) { return v; }
+#else
+RDEV double w_max(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+#endif
+
 // ================================================================================= energy-only filter (K0)
 // Tables of the energy-only grammar (one motif state, no emissions): EnergyModel::calc_BPP (energy_model.hpp:188-193).
 // a: P (by right end), E, M, 1 (by left end), 2 (by right end); b: P, E, M, B (both orientations), 2.  L == 1.
@@ -195,6 +214,7 @@ struct K0Tabs {
   double* Pm;        // P(k,l) times the interior mismatch factor on the inner pair's side (by right end, like P)
   double* bEm;       // outside E(i,j) times the interior mismatch factor on the closing pair's side
   const double* G;   // [32][32] internal[u1+u2] * ninio[|u1-u2|] * kappa0^(u1+u2) for u1,u2 >= 3
+  double *eO, *fO;   // [L+1] power-of-two exponents of the exterior rows O / bO (stored as doubles)
 };
 
 // Interior loops of the energy-only pass.  For u1,u2 >= 3 the loop energy is separable (energy_param.hpp:781-794:
@@ -327,19 +347,25 @@ RDEV void k0_inside_ext(const LinCtx& c, const K0Tabs& t) {
   const DevEnergy& el = LC.el;
   const int L = q.L, lane = lane_id();
   const bool ne = el.no_ene != 0;
-  if (lane == 0) t.O[0] = 1.;
+  if (lane == 0) { t.O[0] = 1.; t.eO[0] = 0.; }
   w_sync();
   for (int j = 1; j <= L; ++j) {
     const unsigned* rj = c.bpr + j * q.mw;
     int dmax = q.W < j ? q.W : j;
+    const int eref = (int)t.eO[j - 1];
     double acc = 0.;
     for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
       int u = u0 + lane;
       if (u <= dmax && row_bit(rj, u))
-        acc += t.O[j - u] * t.P[kidx(q, j, u)] * (ne ? 1. : nl_l_ext(&q, j - u, j - 1, 1));
+        acc += ldexp(t.O[j - u], (int)t.eO[j - u] - eref) * t.P[kidx(q, j, u)] * (ne ? 1. : nl_l_ext(&q, j - u, j - 1, 1));
     }
     acc = w_sum(acc);
-    if (lane == 0) t.O[j] = acc + t.O[j - 1] * LC.k0;
+    if (lane == 0) {
+      double v = acc + t.O[j - 1] * LC.k0;
+      int k = renorm_shift(v);
+      t.O[j] = k ? ldexp(v, -k) : v;
+      t.eO[j] = (double)(eref + k);
+    }
     w_sync();
   }
 }
@@ -348,19 +374,26 @@ RDEV void k0_outside_ext(const LinCtx& c, const K0Tabs& t, double rootw) {
   const DevEnergy& el = LC.el;
   const int L = q.L, lane = lane_id();
   const bool ne = el.no_ene != 0;
-  if (lane == 0) t.bO[L] = rootw;
+  // rootw = 1 / mantissa of O(L); the exponent of 1/Z^ is -eO(L)
+  if (lane == 0) { t.bO[L] = rootw; t.fO[L] = -t.eO[L]; }
   w_sync();
   for (int i = L - 1; i >= 0; --i) {
     const unsigned* ri = q.bp + i * q.mw;
     int dmax = q.W < L - i ? q.W : L - i;
+    const int fref = (int)t.fO[i + 1];
     double acc = 0.;
     for (int u0 = 0; u0 <= dmax; u0 += WARP_N) {
       int u = u0 + lane;
       if (u <= dmax && row_bit(ri, u))
-        acc += t.bO[i + u] * t.P[kidx(q, i + u, u)] * (ne ? 1. : nl_l_ext(&q, i, i + u - 1, 1));
+        acc += ldexp(t.bO[i + u], (int)t.fO[i + u] - fref) * t.P[kidx(q, i + u, u)] * (ne ? 1. : nl_l_ext(&q, i, i + u - 1, 1));
     }
     acc = w_sum(acc);
-    if (lane == 0) t.bO[i] = acc + t.bO[i + 1] * LC.k0;
+    if (lane == 0) {
+      double v = acc + t.bO[i + 1] * LC.k0;
+      int k = renorm_shift(v);
+      t.bO[i] = k ? ldexp(v, -k) : v;
+      t.fO[i] = (double)(fref + k);
+    }
     w_sync();
   }
 }
@@ -408,7 +441,7 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* s
   if (gP) {
     if (gB) bP += b2 * (ne ? 1. : nl_l_ext(&q, i, j - 1, 0) * el.mlintern);
     if (ok_P(q, i - 1, d + 2)) bP += t.bP[kidx(q, i - 1, d + 2)] * LC.k0sq * (ne ? 1. : nl_l_loop(&q, i - 1, j, i, j - 1));
-    bP += t.O[i] * t.bO[j] * (ne ? 1. : nl_l_ext(&q, i, j - 1, 1));
+    bP += ldexp(t.O[i] * t.bO[j], (int)(t.eO[i] + t.fO[j])) * (ne ? 1. : nl_l_ext(&q, i, j - 1, 1));
     // enclosing pairs: this cell is the inner pair (k=i,l=j) of E(i',j')
     const int C = c.Ceff;
     const int hi = W < d + C + 2 ? W : d + C + 2;
@@ -460,6 +493,7 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* s
 struct CTabs {
   double *aP, *aE, *aM, *a1, *a2, *aLl, *aLr, *aO;          // aP, a2, aLr by right end; the rest by left end
   double *bP, *bEl, *bEr, *bM, *bBl, *bBr, *b2, *bL, *bO;   // bEr, bBr by right end; channel c at + c*bch (bO: + c*boch)
+  double *eO, *fO;   // [L+1] power-of-two exponents of the exterior rows aO / bO (all channels share fO)
   unsigned bch, boch;
 };
 
@@ -919,8 +953,10 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
   double* part = w.partA;
   double* cur = w.curA;
   for (int s = lane; s < S; s += WARP_N) t.aO[s] = (s == h.s00) ? 1. : 0.;
+  if (lane == 0) t.eO[0] = 0.;
   w_sync();
   for (int j = 1; j <= L; ++j) {
+    const int eref = (int)t.eO[j - 1];   // column j is assembled at the scale of column j-1, then rescaled
     for (int a = lane; a < h.n_split; a += WARP_N) part[a] = 0.;
     w_sync();
     auto flush = [&](int n) {
@@ -930,7 +966,7 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
         double v = part[a];
         for (int pp = 0; pp < n; ++pp) {
           int i = w.bi[pp];
-          v += t.aO[(unsigned)i * S + sl] * t.aP[cidx(q, j, j - i) + sr] * bf[pp];
+          v += ldexp(t.aO[(unsigned)i * S + sl], (int)t.eO[i] - eref) * t.aP[cidx(q, j, j - i) + sr] * bf[pp];
         }
         part[a] = v;
       }
@@ -958,7 +994,15 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
       part[a] = v;
     }
     w_sync();
-    for (int s = lane; s < S; s += WARP_N) t.aO[(unsigned)j * S + s] = cur[s] + seg_sum(part, h.r_off, s);
+    double mx = 0.;
+    for (int s = lane; s < S; s += WARP_N) {
+      double v = cur[s] + seg_sum(part, h.r_off, s);
+      cur[s] = v;
+      mx = fmax(mx, fabs(v));
+    }
+    const int k = renorm_shift(w_max(mx));
+    for (int s = lane; s < S; s += WARP_N) t.aO[(unsigned)j * S + s] = k ? ldexp(cur[s], -k) : cur[s];
+    if (lane == 0) t.eO[j] = (double)(eref + k);
     w_sync();
   }
 }
@@ -981,6 +1025,7 @@ template <int NCH, int MODE = 0> RDEV void lin_outside_ext(const LinCtx& c, cons
   const int S = q.S, L = q.L, lane = lane_id(), NM = w.n_max;
   const bool ne = LC.en.no_ene != 0;
   for (int i = L - 1; i >= 0; --i) {
+    const int fref = (int)t.fO[i + 1];   // row i is assembled at the scale of row i+1, then rescaled
     for (int a = lane; a < h.n_split; a += WARP_N)
       for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
     w_sync();
@@ -993,7 +1038,7 @@ template <int NCH, int MODE = 0> RDEV void lin_outside_ext(const LinCtx& c, cons
         for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
         for (int pp = 0; pp < n; ++pp) {
           int j = w.bi[pp];
-          double term = t.aP[cidx(q, j, j - i) + sr] * bf[pp];
+          double term = ldexp(t.aP[cidx(q, j, j - i) + sr] * bf[pp], (int)t.fO[j] - fref);
           for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bO[ch * t.boch + (unsigned)j * S + s] * term;
         }
         for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
@@ -1022,7 +1067,8 @@ template <int NCH, int MODE = 0> RDEV void lin_outside_ext(const LinCtx& c, cons
       double wt = ld_ro(p.r_w + a * 5 + xr);
       if (fl & 1) wt *= wsr;
       if (i == c.ys && !(fl & LIN_F_START)) wt = 0.;
-      double ac = t.aO[(unsigned)i * S + ch_s];
+      // posterior = b^O(i+1) w a^O(i): mantissas times 2^(fO(i+1) + eO(i))
+      double ac = ldexp(t.aO[(unsigned)i * S + ch_s], fref + (int)t.eO[i]);
       for (int ch = 0; ch < NCH; ++ch) {
         double contrib = t.bO[ch * t.boch + (unsigned)(i + 1) * S + sp] * wt;
         w.partA[ch * NM + pz] = contrib;
@@ -1031,9 +1077,18 @@ template <int NCH, int MODE = 0> RDEV void lin_outside_ext(const LinCtx& c, cons
       }
     }
     w_sync();
+    double mx = 0.;
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) {
+        double v = w.curB[ch * S + s] + seg_sum(w.partA + ch * NM, h.rT_off, s);
+        w.curB[ch * S + s] = v;
+        mx = fmax(mx, fabs(v));
+      }
+    const int k = renorm_shift(w_max(mx));
     for (int s = lane; s < S; s += WARP_N)
       for (int ch = 0; ch < NCH; ++ch)
-        t.bO[ch * t.boch + (unsigned)i * S + s] = w.curB[ch * S + s] + seg_sum(w.partA + ch * NM, h.rT_off, s);
+        t.bO[ch * t.boch + (unsigned)i * S + s] = k ? ldexp(w.curB[ch * S + s], -k) : w.curB[ch * S + s];
+    if (lane == 0) t.fO[i] = (double)(fref + k);
     w_sync();
   }
 }
@@ -1345,11 +1400,12 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
       if (cX) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
     }
     if (cX) {
+      const int xexp = (int)(t.eO[i] + t.fO[j]);   // a^O(i) b^O(j): mantissas times 2^(eO(i) + fO(j))
       for (int pz = lane; pz < h.n_split; pz += WARP_N) {
         int a = ld_ro(h.spR_ord + pz);
         int s = ld_ro(h.sp_tgt + a), sl_ = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
         int sl = ld_ro(h.slot + s);
-        double term = t.aO[(unsigned)i * S + sl_] * (sl ? f1 : f0);
+        double term = ldexp(t.aO[(unsigned)i * S + sl_] * (sl ? f1 : f0), xexp);
         double ac = t.aP[ir + sr];
         for (int ch = 0; ch < NCH; ++ch) {
           double contrib = t.bO[ch * t.boch + (unsigned)j * S + s] * term;

@@ -50,6 +50,7 @@ struct LinLayout {
   unsigned long long masks;  // 4 x (Lmax+2)*mw words: bp, lf, bpr, lfr
   unsigned long long bytes;  // x [Lmax+2], sp3, sp4, sp6 [Lmax+1 each]
   unsigned long long post;   // scanner: linear start / inner / end posteriors, [Lmax+2] each
+  unsigned long long expo;   // power-of-two exponents of the four exterior rows (K0 O, bO; coupled O, bO), [Lmax+2] each
   int Lmax, Wmax, mw, nch, ncnt, mask_words;
   int sm_ctx, sm_misc, sm_pcnt, sm_warp, warp_bytes_in, warp_bytes_out;
 };
@@ -82,6 +83,7 @@ static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int nc
   lay.masks = take(2ull * lay.mask_words);
   lay.bytes = take((4ull * (Lmax + 2) + 7) / 8);
   lay.post = take(3ull * (Lmax + 2));
+  lay.expo = take(4ull * (Lmax + 2));
   lay.stride = o;
   int b = 0;
   auto sm = [&](int bytes) { int r = b; b += (bytes + 15) & ~15; return r; };
@@ -177,11 +179,13 @@ RDEV CTabs lin_tabs(const LinLayout& lay, double* slot) {
   t.bP = slot + lay.bP; t.bEl = slot + lay.bEl; t.bEr = slot + lay.bEr; t.bM = slot + lay.bM; t.bBl = slot + lay.bBl;
   t.bBr = slot + lay.bBr; t.b2 = slot + lay.b2; t.bL = slot + lay.bL; t.bO = slot + lay.bO;
   t.bch = (unsigned)lay.bch; t.boch = (unsigned)lay.boch;
+  t.eO = slot + lay.expo + 2 * (lay.Lmax + 2); t.fO = t.eO + (lay.Lmax + 2);
   return t;
 }
 RDEV K0Tabs lin_k0tabs(const LinLayout& lay, double* slot, const double* G) {
   K0Tabs t0;
   t0.Pm = slot + lay.kPm; t0.bEm = slot + lay.kbEm; t0.G = G;
+  t0.eO = slot + lay.expo; t0.fO = t0.eO + (lay.Lmax + 2);
   t0.P = slot + lay.kP; t0.E = slot + lay.kE; t0.M = slot + lay.kM; t0.o1 = slot + lay.k1; t0.o2 = slot + lay.k2;
   t0.O = slot + lay.kO; t0.bP = slot + lay.kbP; t0.bE = slot + lay.kbE; t0.bM = slot + lay.kbM;
   t0.bBl = slot + lay.kbBl; t0.bBr = slot + lay.kbBr; t0.b2 = slot + lay.kb2; t0.bO = slot + lay.kbO;
@@ -392,7 +396,8 @@ template <int WHICH, int NCH, int MODE = 0> LIN_KERNEL(32, 16) relem_lin_ext_ker
       }
       if (lane_id() == 0) {
         slot[lay.hdr + 0] = Ztt; slot[lay.hdr + 1] = Ztf; slot[lay.hdr + 2] = Zft;
-        const double shift = -(double)L * LC.p.ln_kappa;  // ln Z = ln Z^ - L ln kappa
+        // ln Z = ln(mantissa) + eO(L) ln 2 - L ln kappa
+        const double shift = -(double)L * LC.p.ln_kappa + t.eO[L] * 0.6931471805599453;
         a.out.Z[n * 3 + 0] = log(Ztt) + shift;
         a.out.Z[n * 3 + 1] = Ztf > 0. ? log(Ztf) + shift : NINF;
         a.out.Z[n * 3 + 2] = Zft > 0. ? log(Zft) + shift : NINF;
@@ -416,7 +421,7 @@ template <int WHICH, int NCH, int MODE = 0> LIN_KERNEL(32, 16) relem_lin_ext_ker
         if (lane_id() == 0) { slot[lay.hdr + 3] = 1.; a.flag[n] = 1; }
         return;
       }
-      if (lane_id() == 0 && a.so.ZL) a.so.ZL[n] = log(Ztt) - (double)L * LC.p.ln_kappa;
+      if (lane_id() == 0 && a.so.ZL) a.so.ZL[n] = log(Ztt) - (double)L * LC.p.ln_kappa + t.eO[L] * 0.6931471805599453;
       for (int k = 0; k < 3; ++k) rw[0][k] = 1. / Ztt;
     } else {
       // scanner, start fixed: a sequence in which the motif cannot start anywhere has Z = 0 and no end posterior
@@ -431,6 +436,7 @@ template <int WHICH, int NCH, int MODE = 0> LIN_KERNEL(32, 16) relem_lin_ext_ker
       if (s == h.s0M1) v = rw[ch][2];
       t.bO[ch * t.boch + (unsigned)L * S + s] = v;
     }
+    if (lane_id() == 0) t.fO[L] = -t.eO[L];   // root weights are 1 / mantissa sums
     return;
   }
   if (WHICH == 3) {

@@ -30,8 +30,18 @@ def emu_lib():
     the product): the same .cu/.cuh files compiled by g++ with -DRELEM_HOST_EMU."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if not _newer(EMU_LIB, srcs):
-        subprocess.check_call(["make", "-C", EMU_DIR, "-s"])
+        subprocess.check_call(["make", "-C", EMU_DIR, "-s", "librelem_emu.so"])
     return EMU_LIB
+
+
+@pytest.fixture(scope="session")
+def emu_renorm_lib(emu_lib):
+    """the emulation built with tiny exterior-row rescaling thresholds (see tests/emu/Makefile)"""
+    p = os.path.join(EMU_DIR, "librelem_emu_renorm.so")
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    if not _newer(p, srcs):
+        subprocess.check_call(["make", "-C", EMU_DIR, "-s", "librelem_emu_renorm.so"])
+    return p
 
 
 @pytest.fixture(scope="session")

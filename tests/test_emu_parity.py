@@ -24,6 +24,16 @@ def test_scan_emulated(name, emu_lib):
     caselib.check_scan(case, ctx)
 
 
+@pytest.mark.parametrize("name", ["m0", "ragged"])
+def test_exterior_row_rescaling(name, emu_renorm_lib):
+    """exterior rows are mantissa + power-of-two exponent per position; with the thresholds at 0.5 / 2 every column is
+    rescaled and E-step and scan must still match the reference"""
+    case = caselib.load_case(name)
+    ctx = caselib.make_ctx(case, lib=emu_renorm_lib)
+    caselib.check_estep(case, ctx)
+    caselib.check_scan(case, ctx)
+
+
 def test_no_rss_is_refused(emu_lib):
     case = caselib.load_case("m2")
     ctx = caselib.make_ctx(case, lib=emu_lib)
