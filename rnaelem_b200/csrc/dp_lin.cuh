@@ -960,13 +960,19 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
     for (int a = lane; a < h.n_split; a += WARP_N) part[a] = 0.;
     w_sync();
     auto flush = [&](int n) {
+      // bring every candidate's O(i) to the scale of this column: once per candidate, folded into its factors
+      for (int z = lane; z < n; z += WARP_N) {
+        double sc = ldexp(1., (int)t.eO[w.bi[z]] - eref);
+        w.bf0[z] *= sc; w.bf1[z] *= sc;
+      }
+      w_sync();
       for (int a = lane; a < h.n_split; a += WARP_N) {
         int sl = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
         const double* bf = ld_ro(h.slot + ld_ro(h.sp_tgt + a)) ? w.bf1 : w.bf0;
         double v = part[a];
         for (int pp = 0; pp < n; ++pp) {
           int i = w.bi[pp];
-          v += ldexp(t.aO[(unsigned)i * S + sl], (int)t.eO[i] - eref) * t.aP[cidx(q, j, j - i) + sr] * bf[pp];
+          v += t.aO[(unsigned)i * S + sl] * t.aP[cidx(q, j, j - i) + sr] * bf[pp];
         }
         part[a] = v;
       }
@@ -1030,6 +1036,11 @@ template <int NCH, int MODE = 0> RDEV void lin_outside_ext(const LinCtx& c, cons
       for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + a] = 0.;
     w_sync();
     auto flush = [&](int n) {
+      for (int z = lane; z < n; z += WARP_N) {
+        double sc = ldexp(1., (int)t.fO[w.bi[z]] - fref);
+        w.bf0[z] *= sc; w.bf1[z] *= sc;
+      }
+      w_sync();
       for (int pz = lane; pz < h.n_split; pz += WARP_N) {
         int a = ld_ro(h.spL_ord + pz);
         int s = ld_ro(h.sp_tgt + a), sr = ld_ro(h.sp_r + a);
@@ -1038,7 +1049,7 @@ template <int NCH, int MODE = 0> RDEV void lin_outside_ext(const LinCtx& c, cons
         for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
         for (int pp = 0; pp < n; ++pp) {
           int j = w.bi[pp];
-          double term = ldexp(t.aP[cidx(q, j, j - i) + sr] * bf[pp], (int)t.fO[j] - fref);
+          double term = t.aP[cidx(q, j, j - i) + sr] * bf[pp];
           for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bO[ch * t.boch + (unsigned)j * S + s] * term;
         }
         for (int ch = 0; ch < NCH; ++ch) w.partA[ch * NM + pz] = v[ch];
@@ -1400,12 +1411,14 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
       if (cX) { F2 ff = boltz2(tsc); f0 = ff.f0; f1 = ff.f1; }
     }
     if (cX) {
-      const int xexp = (int)(t.eO[i] + t.fO[j]);   // a^O(i) b^O(j): mantissas times 2^(eO(i) + fO(j))
+      // a^O(i) b^O(j): mantissas times 2^(eO(i) + fO(j)), folded into the two Boltzmann factors
+      const double xsc = ldexp(1., (int)(t.eO[i] + t.fO[j]));
+      f0 *= xsc; f1 *= xsc;
       for (int pz = lane; pz < h.n_split; pz += WARP_N) {
         int a = ld_ro(h.spR_ord + pz);
         int s = ld_ro(h.sp_tgt + a), sl_ = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
         int sl = ld_ro(h.slot + s);
-        double term = ldexp(t.aO[(unsigned)i * S + sl_] * (sl ? f1 : f0), xexp);
+        double term = t.aO[(unsigned)i * S + sl_] * (sl ? f1 : f0);
         double ac = t.aP[ir + sr];
         for (int ch = 0; ch < NCH; ++ch) {
           double contrib = t.bO[ch * t.boch + (unsigned)j * S + s] * term;
