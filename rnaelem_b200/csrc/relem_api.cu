@@ -323,6 +323,16 @@ int ready(relem_ctx* c) {
 // ======================================================================================================= ABI
 extern "C" {
 
+// every entry point may be called from a fresh host thread (one thread per context in a multi-GPU process):
+// make the context's GPU current before touching device memory
+static inline bool bind_device(const relem_ctx* c) {
+#ifndef RELEM_HOST_EMU
+  return cudaSetDevice(c->dev) == cudaSuccess;
+#else
+  (void)c; return true;
+#endif
+}
+
 const char* relem_version(void) {
 #ifdef RELEM_HOST_EMU
   return "relem-b200 0.1 (HOST EMULATION - debug only)";
@@ -392,6 +402,7 @@ const char* relem_last_error(const relem_ctx* c) { return c ? c->err.c_str() : g
 
 int relem_set_energy(relem_ctx* c, const char* param, int max_span, int max_iloop, double min_bpp, int no_ene) {
   if (!c || !param) return RELEM_EINVAL;
+  if (!bind_device(c)) return fail(c, RELEM_ECUDA, "cudaSetDevice failed");
   if (max_span < 0 || min_bpp < 0) return fail(c, RELEM_EINVAL, "bad max_span / min_bpp");
   EnergyInts ints;
   std::string name(param);
@@ -411,6 +422,7 @@ int relem_set_energy(relem_ctx* c, const char* param, int max_span, int max_iloo
 
 int relem_set_pattern(relem_ctx* c, const char* pattern, int no_rss, int no_prf) {
   if (!c || !pattern) return RELEM_EINVAL;
+  if (!bind_device(c)) return fail(c, RELEM_ECUDA, "cudaSetDevice failed");
   if (no_rss && no_prf) return fail(c, RELEM_EINVAL, "no-rss, no-profile are exclusive.");
   try {
     c->hmm.build(pattern);
@@ -502,6 +514,7 @@ int relem_energy_get(const relem_ctx* c, const char* name, double* out, int cap)
 
 int relem_set_params(relem_ctx* c, const double* theta_flat, int n_theta, const double lambda[2], double tau) {
   if (!c || !theta_flat || !lambda) return RELEM_EINVAL;
+  if (!bind_device(c)) return fail(c, RELEM_ECUDA, "cudaSetDevice failed");
   if (!c->have_pattern) return fail(c, RELEM_EINVAL, "relem_set_pattern has not been called");
   if (n_theta != c->n_theta) return fail(c, RELEM_EINVAL, "theta size does not match the pattern");
   if (!Dev::h2d(c->d_theta.p, theta_flat, sizeof(double) * n_theta)) return fail(c, RELEM_ECUDA, "theta upload failed");
@@ -575,7 +588,8 @@ static int batch_fill(relem_ctx* c, relem_batch* b, int nseq, const uint8_t* seq
 
 int relem_batch_create(relem_ctx* c, int nseq, const uint8_t* seq_cat, const int64_t* off, const double* ws_cat,
                        const uint8_t* kind, const int32_t* gate, relem_batch** out) {
-  if (!out) return RELEM_EINVAL;
+  if (!out || !c) return RELEM_EINVAL;
+  if (!bind_device(c)) return fail(c, RELEM_ECUDA, "cudaSetDevice failed");
   relem_batch* b = new relem_batch();
   int rc = batch_fill(c, b, nseq, seq_cat, off, ws_cat, kind, gate);
   if (rc) { relem_batch_destroy(c, b); return rc; }
@@ -724,6 +738,7 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
 int relem_estep(relem_ctx* c, int nseq, const uint8_t* seq_cat, const int64_t* off, const double* ws_cat,
                 const uint8_t* kind, const int32_t* gate, relem_estep_out* out) {
   if (!c) return RELEM_EINVAL;
+  if (!bind_device(c)) return fail(c, RELEM_ECUDA, "cudaSetDevice failed");
   // the staging batch lives in the context: its device buffers only grow, so a training loop that calls this
   // once per iteration pays for the copies, not for allocations
   if (!c->staging) c->staging = new relem_batch();

@@ -1,0 +1,71 @@
+"""Run a build of the `RNAelem` command line on a golden CLI case (tests/golden/cli, produced by the unmodified
+reference binary through tests/golden/make_cli_golden.py) and compare every output channel.
+
+Comparison rules: text outside numbers must be identical; Viterbi lines (psihat, rss, mot, motif region) and the
+shuffled negatives must be identical byte for byte; numbers are printed with 6 significant digits by both programs,
+so they must agree to 1e-5 relative (one unit of the last printed digit) or 1e-9 absolute (log posteriors of
+probability-one events print as +-1e-15 noise around 0).  Timing lines are ignored.
+"""
+import json
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CLI_GOLDEN = os.path.join(HERE, "golden", "cli")
+MANIFEST = json.load(open(os.path.join(CLI_GOLDEN, "manifest.json")))
+NUM = re.compile(r"-?(?:inf|nan|\d+\.?\d*(?:[eE][-+]?\d+)?)")
+EXACT_KEYS = ("psihat:", "rss:", "mot:", "motif region:", "seq:", "id:", "pattern:", ">iter", "interim: pattern")
+SKIP = ("wall clock time per eval:", "scan end:")
+RTOL, ATOL = 1e-5, 1e-9
+
+
+def run_case(binary, name, workdir, extra_env=None, extra_args=()):
+    c = MANIFEST[name]
+    cmd = [binary] + ([c["sub"]] if c["sub"] else []) + ["-f", os.path.join(HERE, "golden", "_tmp", c["fastq"]), "-t", "1"]
+    cmd += c["args"] + list(extra_args)
+    if c["model_case"]:
+        cmd += ["-q", os.path.join(CLI_GOLDEN, c["model_case"], "out1.txt")]
+    outs = {k: os.path.join(workdir, "%s_%s.txt" % (name, k)) for k in ("out1", "out2", "out3")}
+    for k, v in outs.items():
+        cmd += ["--" + k, v]
+    env = dict(os.environ)
+    env.update(extra_env or {})
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1200)
+    assert p.returncode == 0, "%s failed (%d): %s" % (name, p.returncode, p.stderr[-2000:])
+    got = {"stderr": p.stderr}
+    for k, v in outs.items():
+        got[k] = open(v).read() if os.path.exists(v) else ""
+    return got
+
+
+def compare_text(want, got, what):
+    wl = [l for l in want.split("\n") if not l.startswith(SKIP)]
+    gl = [l for l in got.split("\n") if not l.startswith(SKIP)]
+    assert len(wl) == len(gl), "%s: %d lines vs %d" % (what, len(wl), len(gl))
+    for n, (a, b) in enumerate(zip(wl, gl)):
+        if a == b:
+            continue
+        assert not a.startswith(EXACT_KEYS) or a.startswith("interim:"), "%s line %d differs:\n%s\n%s" % (what, n, a[:300], b[:300])
+        assert NUM.sub("#", a) == NUM.sub("#", b), "%s line %d: text differs:\n%s\n%s" % (what, n, a[:300], b[:300])
+        for x, y in zip(NUM.findall(a), NUM.findall(b)):
+            if x == y:
+                continue
+            fx, fy = float(x), float(y)
+            if fx != fx:
+                # a read too short for the motif: the reference's end posteriors are -inf - (-inf) = NaN,
+                # librelem reports -inf
+                assert fy != fy or fy == float("-inf"), "%s line %d: %s vs %s" % (what, n, x, y)
+                continue
+            assert abs(fx - fy) <= max(ATOL, RTOL * max(abs(fx), abs(fy))), \
+                "%s line %d (%s): %s vs %s" % (what, n, a[:24], x, y)
+
+
+def check_case(binary, name, workdir, **kw):
+    got = run_case(binary, name, workdir, **kw)
+    d = os.path.join(CLI_GOLDEN, name)
+    for k in ("stderr", "out1", "out2", "out3"):
+        fp = os.path.join(d, k + ".txt")
+        want = open(fp).read() if os.path.exists(fp) else ""
+        compare_text(want, got[k], "%s/%s" % (name, k))
+    return got

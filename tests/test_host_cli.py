@@ -1,0 +1,73 @@
+"""Host side of `RNAelem train / scan` (rnaelem_b200/host) against the reference binary's
+golden outputs.  The CPU half runs the command line linked with the single-thread emulation of the kernel source
+(tests/emu; a debug aid, never the product) so that minibatch order, negatives, Adam and the writers are checked in
+the GPU-less container; the GPU half runs the shipped binary rnaelem_b200/RNAelem (librelem.so, sm_100a)."""
+import os
+import subprocess
+
+import pytest
+
+import clilib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRODUCT = os.path.join(ROOT, "rnaelem_b200", "RNAelem")
+GENNEG = ["genneg_k1", "genneg_k2", "genneg_k3"]
+DP_CASES = ["synth_adam", "trna_softmax", "ragged_train", "ragged_scan"]
+
+
+@pytest.fixture(scope="session")
+def emu_cli(emu_lib):
+    subprocess.check_call(["make", "-C", os.path.dirname(emu_lib), "-s", "RNAelem_emu"])
+    return os.path.join(os.path.dirname(emu_lib), "RNAelem_emu")
+
+
+@pytest.fixture(scope="session")
+def product_cli():
+    assert os.path.exists(PRODUCT), "rnaelem_b200/RNAelem missing: run __graft_entry__.build()"
+    return PRODUCT
+
+
+@pytest.mark.parametrize("name", GENNEG)
+def test_shuffled_negatives_bit_exact(name, product_cli, tmp_path):
+    """gen-neg needs no device: the k-let shuffle + glibc rand() stream must reproduce the reference's negatives"""
+    got = clilib.run_case(product_cli, name, str(tmp_path))
+    assert got["out1"] == open(os.path.join(clilib.CLI_GOLDEN, name, "out1.txt")).read()
+
+
+def test_product_refuses_without_gpu(product_cli, tmp_path):
+    """no CPU path: without a CUDA device the shipped binary must fail loudly, not compute"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    c = clilib.MANIFEST["ragged_scan"]
+    p = subprocess.run([product_cli, "scan", "-f", os.path.join(clilib.HERE, "golden", "_tmp", c["fastq"]),
+                        "-q", os.path.join(clilib.CLI_GOLDEN, "synth_adam", "out1.txt"), "--out1", str(tmp_path / "x")],
+                       capture_output=True, text=True)
+    assert p.returncode == 1 and "no CUDA device" in p.stderr
+
+
+@pytest.mark.parametrize("name", DP_CASES)
+def test_cli_emulated(name, emu_cli, tmp_path):
+    clilib.check_case(emu_cli, name, str(tmp_path))
+
+
+def test_unknown_option_and_subcommand(product_cli):
+    p = subprocess.run([product_cli, "--no-such-flag"], capture_output=True, text=True)
+    assert p.returncode == 1
+    p = subprocess.run([product_cli, "frobnicate", "-f", "x"], capture_output=True, text=True)
+    assert p.returncode == 1 and "unknown sub-command" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", DP_CASES)
+def test_cli_gpu(name, product_cli, tmp_path):
+    clilib.check_case(product_cli, name, str(tmp_path))
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus(product_cli, tmp_path):
+    """minibatch sharded over two contexts + NCCL all-reduce of the partial sums: same trajectory"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    clilib.check_case(product_cli, "synth_adam", str(tmp_path), extra_args=["--gpus", "2"])
