@@ -247,12 +247,23 @@ struct Launch {
   int nslots = 0;
 };
 
+// --no-rss (the linear profile HMM, RNAelem::compute_inside / compute_outside, motif_model.hpp:170-219): the
+// reference walks the exterior row alone -- O(i,s) <- O(i-1,s1) over the right transitions, no base pair anywhere,
+// EnergyModel::set_seq never called (bpp_eff stays 0).  That is the structured model with the band collapsed to
+// span 0 and the base-pair filter off, so the same kernels serve it at a few launches per batch.
+static inline int eff_span(const relem_ctx* c) { return c->no_rss ? 0 : c->max_span; }
+static void apply_mode(relem_ctx* c) {
+  const int filt = (!c->no_rss && c->min_bpp != 0.) ? 1 : 0;
+  c->den.max_span = eff_span(c); c->den.filter = filt;
+  c->denl.max_span = eff_span(c); c->denl.filter = filt;
+}
+
 // choose the number of resident CTAs (= scratch slots) and make sure the scratch fits
 int plan_launch(relem_ctx* c, const relem_batch* b, int nch, bool coupled, const void* kernel, Launch& L,
                 int max_n = 1 << 30) {
   int S = c->flat.S, M = c->flat.M;
   L.c = c;
-  L.lay = make_layout(std::max(1, b->Lmax), c->max_span, S, M, c->n_theta, nch, coupled);
+  L.lay = make_layout(std::max(1, b->Lmax), eff_span(c), S, M, c->n_theta, nch, coupled);
   unsigned long long band = (unsigned long long)NPLANE * (b->Lmax + 1) * (L.lay.Wmax + 1) * (coupled ? S : 1);
   if (band >= (1ull << 31)) return fail(c, RELEM_EINVAL, "band table of one sequence exceeds 2^31 entries");
 #ifdef RELEM_HOST_EMU
@@ -314,7 +325,6 @@ int ready(relem_ctx* c) {
   if (!c->have_energy) return fail(c, RELEM_EINVAL, "relem_set_energy has not been called");
   if (!c->have_pattern) return fail(c, RELEM_EINVAL, "relem_set_pattern has not been called");
   if (!c->have_params) return fail(c, RELEM_EINVAL, "relem_set_params has not been called");
-  if (c->no_rss) return fail(c, RELEM_EINVAL, "the --no-rss linear model is not built in this round");
   return RELEM_OK;
 }
 
@@ -417,6 +427,7 @@ int relem_set_energy(relem_ctx* c, const char* param, int max_span, int max_iloo
   c->max_span = max_span; c->max_iloop = max_iloop; c->min_bpp = min_bpp; c->no_ene = no_ene ? 1 : 0;
   if (!upload_energy(c)) return fail(c, RELEM_ENOMEM, "energy upload failed");
   c->have_energy = true;
+  apply_mode(c);
   return RELEM_OK;
 }
 
@@ -433,6 +444,7 @@ int relem_set_pattern(relem_ctx* c, const char* pattern, int no_rss, int no_prf)
     return fail(c, RELEM_EINVAL, "search pattern must not include pair when no-rss mode");
   c->flat.from(c->hmm);
   c->no_rss = no_rss ? 1 : 0; c->no_prf = no_prf ? 1 : 0;
+  if (c->have_energy) apply_mode(c);
   c->n_theta = c->hmm.n_theta();
   std::vector<int> n2s;
   for (auto& r : c->hmm.n2s) n2s.insert(n2s.end(), r.begin(), r.end());
@@ -643,7 +655,7 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
     lin::LinLaunch ll;
     ll.h = c->dlh; ll.p = c->dlp; ll.en = c->den; ll.el = c->denl;
     ll.kappa0 = std::exp(-0.3);
-    ll.b = bv; ll.Lmax = b->Lmax; ll.max_span = c->max_span; ll.out = eo;
+    ll.b = bv; ll.Lmax = b->Lmax; ll.max_span = eff_span(c); ll.out = eo;
     ll.flag = c->d_flag.as<unsigned char>();
     ll.nch = (out->ENo || out->ENx || out->EH) ? 2 : 1;
     ll.max_slots = 0;
@@ -693,6 +705,8 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
     t.stop();
   }
   bv = batch_view(b);
+  // the reference never runs the base-pair filter in --no-rss mode: EnergyModel::bpp_eff() keeps its initial 0
+  if (c->no_rss && !Dev::zero(c->d_eff.p, sizeof(double) * nseq)) return fail(c, RELEM_ECUDA, "bpp_eff reset failed");
   {
     Timer t(c, "relem_reduce_kernel");
     const int* gp = b->has_gate ? b->d_gate.as<int>() : nullptr;
@@ -751,6 +765,7 @@ int relem_bpp(relem_ctx* c, relem_batch* b, int64_t* moff, uint8_t* bp_ok, uint8
               double* bpp_eff, double* lnZ) {
   if (!c || !b || !moff) return RELEM_EINVAL;
   if (!c->have_energy) return fail(c, RELEM_EINVAL, "relem_set_energy has not been called");
+  if (c->no_rss) return fail(c, RELEM_EINVAL, "no base-pair filter in --no-rss mode");
   c->timing.clear();
   const int nseq = b->nseq;
   std::vector<long long> mo(nseq + 1, 0);
@@ -856,7 +871,7 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
     lin::LinScanLaunch ll;
     ll.h = c->dlh; ll.p = c->dlp; ll.en = c->den; ll.el = c->denl;
     ll.kappa0 = std::exp(-0.3);
-    ll.b = bv; ll.Lmax = b->Lmax; ll.max_span = c->max_span; ll.so = so;
+    ll.b = bv; ll.Lmax = b->Lmax; ll.max_span = eff_span(c); ll.so = so;
     ll.flag = c->d_flag.as<unsigned char>();
     ll.max_slots = 0;
     if (const char* e = std::getenv("RELEM_MAX_SLOTS")) ll.max_slots = std::max(1, std::atoi(e));

@@ -34,11 +34,13 @@ def test_exterior_row_rescaling(name, emu_renorm_lib):
     caselib.check_scan(case, ctx)
 
 
-def test_no_rss_is_refused(emu_lib):
+def test_no_rss_linear_model(emu_lib):
+    """--no-rss (motif_model.hpp:170-219): exterior-row recursion only; fixture m2 comes from the reference"""
     case = caselib.load_case("m2")
     ctx = caselib.make_ctx(case, lib=emu_lib)
+    caselib.check_estep(case, ctx)
+    caselib.check_scan(case, ctx)
     seqs, wss = caselib.scan_inputs(case)
     sc, off, wc = rb.pack_batch(seqs, wss)
-    b = ctx.batch(sc, off, wc)
     with pytest.raises(rb.RelemError):
-        ctx.estep_run(b)
+        ctx.bpp(ctx.batch(sc, off, wc))   # no base-pair filter in this mode
