@@ -247,7 +247,6 @@ def main_own(args):
         tm = ctx.timing()
         kernel_ms.append(sum(t[1] for t in tm if t[0] in ("relem_estep_lin_kernel", "relem_estep_kernel")))
         kname = max((t for t in tm if t[2] > 0), key=lambda t: t[1])[0]
-        phases = {t[0][6:]: round(t[1], 4) for t in tm if t[0].startswith("phase:")}
         launches += sum(t[2] for t in tm)
     barrier()
     t1 = time.perf_counter()
@@ -298,10 +297,21 @@ def main_own(args):
         else:
             peak, which = 6650.0, "fallback"
         achieved = step_bytes / (kms * 1e-3) / 1e9
-        traffic = None
+        traffic, issue = None, None
         tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+        clocks = sampler.summary()
         if os.path.exists(tpath):
-            traffic = int(json.load(open(tpath))["dram_bytes_per_sequence_evaluation"] * 2 * npos)
+            prof = json.load(open(tpath))
+            traffic = int(prof["dram_bytes_per_sequence_evaluation"] * 2 * npos)
+            # the recursion is sparse gather work: the resource that binds is warp-instruction issue, not HBM or
+            # the fp64 pipe.  instructions per sequence-evaluation come from the ncu pass of the same workload
+            # (smsp__inst_executed.sum), the rate from this run's device time; peak = SMs x 4 schedulers x clock.
+            sm = torch.cuda.get_device_properties(local).multi_processor_count
+            mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+            ach = prof["warp_instructions_per_sequence_evaluation"] * 2 * npos / (kms * 1e-3)
+            pk = sm * 4 * mhz * 1e6
+            issue = {"achieved": ach, "peak": pk, "unit": "warp-instructions/s", "frac": ach / pk,
+                     "source": "profiles/r1_dram_traffic.json (ncu smsp__inst_executed.sum per sequence-evaluation)"}
         line = {"metric": "dp_cells_per_s", "value": value, "unit": "dp_cells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -310,12 +320,12 @@ def main_own(args):
                 "e2e": {"value": e2e, "unit": "dp_cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": 1e3 * dt_e2e / args.steps, "kernel_ms_per_step": float(np.mean(e2e_kernel_ms))},
                 "gpu_launches": int(launches),
-                "clocks": sampler.summary(),
+                "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": which,
                              "kernel_ms": kms, "algorithmic_bytes_per_launch": int(step_bytes),
                              "note": "one 'launch' = the whole wavefront of phase kernels over the step's batch"},
-                "phase_share": phases,
+                "issue": issue,
                 "scan": {"value": world * nscan / dt_scan, "unit": "seqs/s", "sample": "%d x %d nt per GPU" % (nscan, SEQ_LEN)}}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

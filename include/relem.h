@@ -34,6 +34,13 @@ typedef struct relem_batch relem_batch;
 #define RELEM_POS_WITHOUT 0 /* user sequence flagged "does not contain the motif": Zx = Z(ari=0,nasi=1) */
 #define RELEM_POS_WITH 1    /* user sequence flagged "contains the motif" (quality string ends in '!')    */
 #define RELEM_NEG 2         /* shuffled negative: Zx = Z(0,1); only Z(1,1) must be finite                 */
+/* --lik-ratio objective (motif_trainer.hpp:156-202): every sequence contrasts Z(1,1) with Z(1,0) and both must be
+ * finite.  A user sequence flagged "contains the motif" is RELEM_POS_WITH (Zo = Z(1,1), Zx = Z(1,0)); one flagged
+ * "does not" and every shuffled negative have the roles swapped (Zo = Z(1,0), Zx = Z(1,1)): their fn, EN_diff and
+ * EH_diff contributions enter the batch sums with the opposite sign.  The per-sequence detail arrays keep the
+ * (1,1)-then-(1,0) order for these kinds. */
+#define RELEM_LR_WITHOUT 3  /* user sequence, counts towards sum_eff                                      */
+#define RELEM_LR_NEG 4      /* shuffled negative                                                          */
 
 const char* relem_version(void);
 

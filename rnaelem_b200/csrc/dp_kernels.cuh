@@ -251,7 +251,7 @@ RELEM_KERNEL relem_estep_kernel(ModelView nullm, ModelView m, BatchView b, SlotL
     double rM2 = h.s0M2 >= 0 ? otab[L * S + h.s0M2] : NINF;
     double rM1 = h.s0M1 >= 0 ? otab[L * S + h.s0M1] : NINF;
     root[0] = exp(r00 - Ztt); root[1] = exp(rM2 - Ztt); root[2] = exp(rM1 - Ztt);
-    if (kind == 1) { root[3] = 0.; root[4] = exp(rM2 - Ztf); root[5] = exp(rM1 - Ztf); }
+    if (kind == 1 || kind >= 3) { root[3] = 0.; root[4] = exp(rM2 - Ztf); root[5] = exp(rM1 - Ztf); }
     else { root[3] = (Zft > NINF) ? exp(r00 - Zft) : 0.; root[4] = 0.; root[5] = 0.; }
     Counts cn; cn.G = G; cn.ENp = sm.en; cn.Pys = cn.Pyi = cn.Pye = nullptr; cn.n_theta = NT; cn.ML = m.h.M * L;
     double eh[4];
@@ -306,11 +306,15 @@ RELEM_KERNEL relem_reduce_kernel(int nseq, int NT, const unsigned char* kind, Es
     if (t == 2) { if (sk == 1) acc += 1.; continue; }
     if (sk) continue;
     int kd = kind[n];
-    if (t == 0) acc += out.Z[n * 3 + 0] - (kd == 1 ? out.Z[n * 3 + 1] : out.Z[n * 3 + 2]);
-    else if (t == 1) { if (kd != 2) acc += out.bpp_eff[n]; }
-    else if (t < 7) acc += out.EH[n * 4 + (t - 3)];
-    else if (t < 7 + NT) acc += out.ENo[(long long)n * NT + (t - 7)];
-    else acc += out.ENx[(long long)n * NT + (t - 7 - NT)];
+    // --lik-ratio kinds 3 / 4 (motif_trainer.hpp:156-202): the pair Z(1,1) / Z(1,0) with the roles of Zo and Zx
+    // swapped, i.e. the kind-1 terms with the opposite sign
+    const bool with_pair = kd == 1 || kd >= 3;
+    const double sg = kd >= 3 ? -1. : 1.;
+    if (t == 0) acc += sg * (out.Z[n * 3 + 0] - (with_pair ? out.Z[n * 3 + 1] : out.Z[n * 3 + 2]));
+    else if (t == 1) { if (kd != 2 && kd != 4) acc += out.bpp_eff[n]; }
+    else if (t < 7) acc += sg * out.EH[n * 4 + (t - 3)];
+    else if (t < 7 + NT) acc += sg * out.ENo[(long long)n * NT + (t - 7)];
+    else acc += sg * out.ENx[(long long)n * NT + (t - 7 - NT)];
   }
   red[CTA_TID] = acc;
   CTA_SYNC();

@@ -583,7 +583,7 @@ static int batch_fill(relem_ctx* c, relem_batch* b, int nseq, const uint8_t* seq
   b->gate.assign(nseq, -1);
   if (gate) { b->gate.assign(gate, gate + nseq); b->has_gate = true; }
   for (int n = 0; n < nseq; ++n) {
-    if (b->kind[n] > 2) { return fail(c, RELEM_EINVAL, "bad sequence kind"); }
+    if (b->kind[n] > 4) { return fail(c, RELEM_EINVAL, "bad sequence kind"); }
     if (b->gate[n] >= nseq || b->gate[n] == n) { return fail(c, RELEM_EINVAL, "bad gate index"); }
   }
   // the caller's buffers go to the device as they are (no staging copies)

@@ -407,7 +407,7 @@ template <int WHICH, int NCH, int MODE = 0> LIN_KERNEL(32, 16) relem_lin_ext_ker
       // NCH = 1 carries their difference
       double o0 = 1. / Ztt;
       double x00 = 0., xM = 0.;
-      if (kind == 1) xM = 1. / Ztf;
+      if (kind == 1 || kind >= 3) xM = 1. / Ztf;
       else x00 = Zft > 0. ? 1. / Zft : 0.;
       if (NCH == 2) {
         rw[0][0] = o0; rw[0][1] = o0; rw[0][2] = o0;

@@ -116,7 +116,6 @@ class RNAelemTrainer {
   void set_fq_name(const std::string& f) { qr_.open(f); }
   void set_conditions(int max_iter, double /*epsilon: L-BFGS-B only*/, double lambda_init, int kmer_shuf, int batch_size) {
     check(!(mode_ & TR_NO_SHUFFLE), "--no-shuffle (L-BFGS-B) training is not available in this build");
-    check(!(mode_ & TR_LIK_RATIO), "--lik-ratio training is not available in this build");
     max_iter_ = max_iter; kmer_shuf_ = kmer_shuf; lambda_init_ = lambda_init;
     adam_.set_hp(0, 0, 0.1, 0.9, 0.999, 1.e-8);
     qr_.set_batch_size(batch_size);
@@ -162,11 +161,12 @@ class RNAelemTrainer {
       check(r.seq.size() + 1 == r.qual.size(), "bad seq format.", r.id, r.seq.size(), r.qual.size());
       bool with_motif = quality_to_weights(r.qual, w);
       int me = b.n();
-      b.add(r.seq, w, with_motif ? RELEM_POS_WITH : RELEM_POS_WITHOUT, -1, r.id);
+      const bool lr = (mode_ & TR_LIK_RATIO) != 0;   // likelihood-ratio objective: motif_trainer.hpp:156-202
+      b.add(r.seq, w, with_motif ? RELEM_POS_WITH : lr ? RELEM_LR_WITHOUT : RELEM_POS_WITHOUT, -1, r.id);
       std::string neg = shuffled_negative(codes_to_text(r.seq), kmer_shuf_, cnt_);
       VI nc(neg.size());
       for (size_t k = 0; k < neg.size(); ++k) nc[k] = base_code(neg[k]);
-      b.add(nc, V(neg.size(), 0.), RELEM_NEG, me, r.id);   // all-zero qualities -> weight ln(0.01/0.01) = 0
+      b.add(nc, V(neg.size(), 0.), lr ? RELEM_LR_NEG : RELEM_NEG, me, r.id);   // all-zero qualities -> weight ln(0.01/0.01) = 0
     }
     dev_.push_params(*motif_);
 

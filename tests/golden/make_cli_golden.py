@@ -29,6 +29,9 @@ CASES = {
     "ragged_scan": ("scan", "ragged.fq", [], "synth_adam"),
     # --no-rss through the '_' pattern spelling (application.hpp:402-407): linear profile HMM, model file says no-rss: 1
     "norss_adam": (None, "ragged.fq", ["-m", "__*_", "--max-iter", "6", "--batch-size", "3"], None),
+    # likelihood-ratio objective; the second and fifth read of ragged.fq are flagged "without motif"
+    "ragged_likratio": ("train", "ragged.fq", ["-m", "(.*)", "--lik-ratio", "--max-iter", "4", "--batch-size", "-1",
+                                               "--lambda-init", "0.4"], None),
     # shuffled negatives only
     "genneg_k2": ("gen-neg", "ragged.fq", ["-i", "3"], None),
     "genneg_k3": ("gen-neg", "synth.fq", ["-i", "2", "--kmer-shuf", "3"], None),

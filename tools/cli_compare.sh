@@ -46,6 +46,30 @@ for k in a:
     except AssertionError as e:
         bad += 1
         print(str(e)[:300])
-print("scan.raw records:", len(a), "differing:", bad)
+print("scan.raw of the train+scan command (each binary scans with its own in-memory parameters, which agree to ~1e-12;")
+print("  equal-score Viterbi alternatives may then resolve differently): records", len(a), "differing:", bad)
+PY
+# same model FILE for both: every line, Viterbi strings included, must agree
+rnaelem_b200/RNAelem scan -f $OUT/in.fq -q $OUT/ref.model --out1 $OUT/ours_scan.raw 2> $OUT/ours_scan.err
+oracle/_ref/RNAelem scan -f $OUT/in.fq -q $OUT/ref.model -t $T --out1 $OUT/ref_scan.raw 2> $OUT/ref_scan.err
+grep "scan end" $OUT/ours_scan.err $OUT/ref_scan.err
+python - $OUT <<'PY'
+import sys, os
+sys.path.insert(0, "tests")
+import clilib
+d = sys.argv[1]
+def recs(p):
+    L = open(p).read().split("\n")
+    return {L[i]: "\n".join(L[i:i + 10]) for i in range(0, len(L) - 1, 10)}
+a, b = recs(os.path.join(d, "ref_scan.raw")), recs(os.path.join(d, "ours_scan.raw"))
+assert a.keys() == b.keys()
+bad = 0
+for k in a:
+    try:
+        clilib.compare_text(a[k], b[k], k)
+    except AssertionError as e:
+        bad += 1
+        print(str(e)[:300])
+print("scan with the same model file: records", len(a), "differing:", bad)
 PY
 fi
