@@ -8,10 +8,10 @@ There is no CPU implementation here: importing works anywhere, but creating a co
 GPU raises RelemError.
 """
 from .binding import (RelemError, Context, load_library, lib_path, EstepResult, ScanResult,  # noqa: F401
-                      POS_WITHOUT, POS_WITH, NEG)
+                      POS_WITHOUT, POS_WITH, NEG, LR_WITHOUT, LR_NEG)
 from .hostio import (read_fastq, read_model, seq_codes, quality_to_ws, model_theta_flat,  # noqa: F401
                      band_cells, pack_batch)
 
 __all__ = ["RelemError", "Context", "load_library", "lib_path", "EstepResult", "ScanResult", "read_fastq",
            "read_model", "seq_codes", "quality_to_ws", "model_theta_flat", "band_cells", "pack_batch",
-           "POS_WITHOUT", "POS_WITH", "NEG"]
+           "POS_WITHOUT", "POS_WITH", "NEG", "LR_WITHOUT", "LR_NEG"]

@@ -5,6 +5,7 @@ import os
 import numpy as np
 
 POS_WITHOUT, POS_WITH, NEG = 0, 1, 2
+LR_WITHOUT, LR_NEG = 3, 4   # --lik-ratio kinds (include/relem.h)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <future>
 #include <thread>
 
 #include "elem_host.hpp"
@@ -154,19 +155,34 @@ class RNAelemTrainer {
     sum_eff_ = 0.;
     qr_.next_batch();
 
-    PackedBatch b;
-    V w;
+    // reads of the minibatch in reader order; weights and negatives are per-read work done on several host threads
+    std::vector<const Read*> rs;
     while (!qr_.batch_done()) {
       const Read& r = qr_.get();
       check(r.seq.size() + 1 == r.qual.size(), "bad seq format.", r.id, r.seq.size(), r.qual.size());
-      bool with_motif = quality_to_weights(r.qual, w);
+      rs.push_back(&r);
+    }
+    const int nr = int(rs.size());
+    std::vector<V> wv(nr);
+    std::vector<VI> negv(nr);
+    std::vector<char> flagged(nr, 0);
+    std::vector<std::string> fail(nr);
+    const int kshuf = kmer_shuf_, iter = cnt_;
+    parallel_for(nr, [&, kshuf, iter](int i) {
+      try {
+        flagged[i] = quality_to_weights(rs[i]->qual, wv[i]) ? 1 : 0;
+        std::string neg = shuffled_negative(codes_to_text(rs[i]->seq), kshuf, iter);
+        negv[i].resize(neg.size());
+        for (size_t k = 0; k < neg.size(); ++k) negv[i][k] = base_code(neg[k]);
+      } catch (std::exception& e) { fail[i] = e.what(); }
+    });
+    for (auto& f : fail) if (!f.empty()) throw std::runtime_error(f);
+    PackedBatch b;
+    const bool lr = (mode_ & TR_LIK_RATIO) != 0;   // likelihood-ratio objective: motif_trainer.hpp:156-202
+    for (int i = 0; i < nr; ++i) {
       int me = b.n();
-      const bool lr = (mode_ & TR_LIK_RATIO) != 0;   // likelihood-ratio objective: motif_trainer.hpp:156-202
-      b.add(r.seq, w, with_motif ? RELEM_POS_WITH : lr ? RELEM_LR_WITHOUT : RELEM_POS_WITHOUT, -1, r.id);
-      std::string neg = shuffled_negative(codes_to_text(r.seq), kmer_shuf_, cnt_);
-      VI nc(neg.size());
-      for (size_t k = 0; k < neg.size(); ++k) nc[k] = base_code(neg[k]);
-      b.add(nc, V(neg.size(), 0.), lr ? RELEM_LR_NEG : RELEM_NEG, me, r.id);   // all-zero qualities -> weight ln(0.01/0.01) = 0
+      b.add(rs[i]->seq, wv[i], flagged[i] ? RELEM_POS_WITH : lr ? RELEM_LR_WITHOUT : RELEM_POS_WITHOUT, -1, rs[i]->id);
+      b.add(negv[i], V(negv[i].size(), 0.), lr ? RELEM_LR_NEG : RELEM_NEG, me, rs[i]->id);   // qualities all 0 -> weight 0
     }
     dev_.push_params(*motif_);
 
@@ -261,14 +277,45 @@ class RNAelemScanner {
       std::string rss;
       V en;
     };
-    // rounds of nw * chunk reads: rank k scans its contiguous block, the host prints the blocks in input order
+    // the ten lines of reads [n0, n1) of one rank's block (motif_scanner.hpp:240-251)
+    auto format_records = [&node, M](const Result& r, int n0, int n1) {
+      std::ostringstream os;
+      for (int n = n0; n < n1; ++n) {
+        size_t a = size_t(r.b.off[n]), L = size_t(r.b.off[n + 1]) - a;
+        VI psi(r.psihat.begin() + a, r.psihat.begin() + a + L), codes(r.b.seq.begin() + a, r.b.seq.begin() + a + L);
+        std::string mot;
+        for (int h : psi) mot += (h == 0 || h == M - 1) ? ' ' : node[h];
+        put_line(os, "id:", r.b.id[n]);
+        put_line(os, "start:", V(r.ps.begin() + a, r.ps.begin() + a + L));
+        put_line(os, "end:", V(r.pe.begin() + a + n, r.pe.begin() + a + n + L + 1));
+        put_line(os, "inner:", V(r.pi.begin() + a, r.pi.begin() + a + L));
+        put_line(os, "psihat:", psi);
+        put_line(os, "motif region:", r.ys[n], "-", r.ye[n]);
+        put_line(os, "exist prob:", r.exist[n]);
+        put_line(os, "seq:", codes_to_text(codes));
+        put_line(os, "rss:", r.rss.substr(a, L));
+        put_line(os, "mot:", mot);
+      }
+      return os.str();
+    };
+    // Rounds of nw * chunk reads: rank k scans its contiguous block.  Turning ~600 doubles per read into text costs
+    // about as much host time as the GPU needs for the DP, so the records of a round are formatted by a few host
+    // threads while the GPUs already work on the next round, and written in input order one round behind.
+    const int n_fmt = int(std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+    std::vector<std::future<std::string>> pending;
+    auto drain = [&] {
+      std::ostream& os = out_.at(out_id_);
+      for (auto& f : pending) os << f.get();
+      os.flush();
+      pending.clear();
+    };
     for (size_t base = 0; base < reads.size(); base += size_t(nw) * chunk_) {
       long n_round = long(std::min(reads.size() - base, size_t(nw) * chunk_));
-      std::vector<Result> res(nw);
+      auto res = std::make_shared<std::vector<Result>>(nw);
       dev_.each([&](int k) {
         long a, z;
         shard_range(n_round, nw, k, a, z);
-        Result& r = res[k];
+        Result& r = (*res)[k];
         V w;
         for (long q = a; q < z; ++q) {
           const Read& rd = *reads[base + q];
@@ -287,26 +334,17 @@ class RNAelemScanner {
         o.rss = &r.rss[0]; o.Ys = r.ys.data(); o.Ye = r.ye.data(); o.exist_prob = r.exist.data(); o.EN = r.en.data();
         dev_.ok(k, relem_scan(dev_.ctx(k), ns, r.b.seq.data(), r.b.off.data(), r.b.ws.data(), &o), "relem_scan");
       });
-      for (Result& r : res) {
-        for (int n = 0; n < r.b.n(); ++n) {
-          size_t a = size_t(r.b.off[n]), L = size_t(r.b.off[n + 1]) - a;
-          VI psi(r.psihat.begin() + a, r.psihat.begin() + a + L), codes(r.b.seq.begin() + a, r.b.seq.begin() + a + L);
-          std::string mot;
-          for (int h : psi) mot += (h == 0 || h == M - 1) ? ' ' : node[h];
-          out_.dat(out_id_, "id:", r.b.id[n]);
-          out_.dat(out_id_, "start:", V(r.ps.begin() + a, r.ps.begin() + a + L));
-          out_.dat(out_id_, "end:", V(r.pe.begin() + a + n, r.pe.begin() + a + n + L + 1));
-          out_.dat(out_id_, "inner:", V(r.pi.begin() + a, r.pi.begin() + a + L));
-          out_.dat(out_id_, "psihat:", psi);
-          out_.dat(out_id_, "motif region:", r.ys[n], "-", r.ye[n]);
-          out_.dat(out_id_, "exist prob:", r.exist[n]);
-          out_.dat(out_id_, "seq:", codes_to_text(codes));
-          out_.dat(out_id_, "rss:", r.rss.substr(a, L));
-          out_.dat(out_id_, "mot:", mot);
-        }
-        for (int k = 0; k < nth && !r.en.empty(); ++k) en_total[k] += r.en[k];
+      drain();   // the previous round's text was produced while this round ran on the GPUs
+      for (int k = 0; k < nw; ++k) {
+        const int ns = (*res)[k].b.n(), per = (ns + n_fmt - 1) / std::max(1, n_fmt);
+        for (int n0 = 0; n0 < ns; n0 += per)
+          pending.push_back(std::async(std::launch::async, [res, k, n0, per, ns, format_records] {
+            return format_records((*res)[k], n0, std::min(ns, n0 + per));
+          }));
+        for (int t = 0; t < nth && !(*res)[k].en.empty(); ++t) en_total[t] += (*res)[k].en[t];
       }
     }
+    drain();
     VV en_rows;
     size_t k = 0;
     for (const V& row : model.theta) { en_rows.push_back(V(en_total.begin() + k, en_total.begin() + k + row.size())); k += row.size(); }

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <limits>
@@ -28,6 +29,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace relem {
@@ -274,12 +276,18 @@ std::string klet_shuffle(const std::string& s, int k, Rand&& rnd) {
 }
 
 // the trainer's negative for one positive at objective evaluation `iter` (motif_trainer.hpp:145-152): glibc's
-// generator seeded with (count of the first base) + iter.  Not thread-safe (srand/rand), as in the reference,
-// where it runs under the input mutex.
+// generator seeded with (count of the first base) + iter.  The reference calls srand()/rand() under its input mutex;
+// here the same stream comes from glibc's re-entrant interface (srand/rand ARE srandom/random on the default
+// 128-byte additive-feedback state, which initstate_r/random_r reproduce on a private state), so the negatives of a
+// minibatch can be generated by several host threads and are still the reference's sequences bit for bit.
 inline std::string shuffled_negative(const std::string& s, int k, int iter) {
   check(s.size() < 9999, "sequence too long for negative generation:", s.size());   // const_options.hpp MAX_SEQLEN
-  std::srand(unsigned(int(std::count(s.begin(), s.end(), s.empty() ? '\0' : s[0])) + iter));
-  return klet_shuffle(s, k, [] { return long(std::rand()); });
+  struct random_data rd;
+  char state[128];
+  std::memset(&rd, 0, sizeof rd);
+  std::memset(state, 0, sizeof state);
+  initstate_r(unsigned(int(std::count(s.begin(), s.end(), s.empty() ? '\0' : s[0])) + iter), state, sizeof state, &rd);
+  return klet_shuffle(s, k, [&rd] { int32_t v = 0; random_r(&rd, &v); return long(v); });
 }
 
 // --------------------------------------------------------------------------------------------- motif model
@@ -568,6 +576,17 @@ class Adam {
     } while (!(gg < (y + 1.) * 1.e-8) && t_ < max_iter);
   }
 };
+
+// f(i) for i in [0, n) on a few host threads (f must only touch slot i)
+template <class F>
+void parallel_for(int n, F f) {
+  const int nt = int(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())));
+  if (n < 64 || nt == 1) { for (int i = 0; i < n; ++i) f(i); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([=] { for (int i = t; i < n; i += nt) f(i); });
+  for (auto& x : th) x.join();
+}
 
 // contiguous shard of `total` items for worker k of n (ArrayJobManager::assigned_range, arrayjob_manager.hpp:141-149)
 inline void shard_range(long total, int n, int k, long& from, long& to) {
