@@ -32,6 +32,8 @@ CASES = {
     # likelihood-ratio objective; the second and fifth read of ragged.fq are flagged "without motif"
     "ragged_likratio": ("train", "ragged.fq", ["-m", "(.*)", "--lik-ratio", "--max-iter", "4", "--batch-size", "-1",
                                                "--lambda-init", "0.4"], None),
+    # scan of 200-nt reads with a model FILE: same parameter bits on both sides -> Viterbi strings exact
+    "synth_scan": ("scan", "synth.fq", [], "synth_adam"),
     # shuffled negatives only
     "genneg_k2": ("gen-neg", "ragged.fq", ["-i", "3"], None),
     "genneg_k3": ("gen-neg", "synth.fq", ["-i", "2", "--kmer-shuf", "3"], None),

@@ -12,7 +12,7 @@ import clilib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PRODUCT = os.path.join(ROOT, "rnaelem_b200", "RNAelem")
 GENNEG = ["genneg_k1", "genneg_k2", "genneg_k3"]
-DP_CASES = ["synth_adam", "trna_softmax", "ragged_train", "ragged_scan", "norss_adam", "ragged_likratio"]
+DP_CASES = ["synth_adam", "trna_softmax", "ragged_train", "ragged_scan", "norss_adam", "ragged_likratio", "synth_scan"]
 
 
 @pytest.fixture(scope="session")
