@@ -257,12 +257,16 @@ template <class V> RDEV void enum_O(const ModelView& m, const SeqView& q, int j,
 }
 
 // ------------------------------------------------------------------------------------------- constraints
+// outside_cells(): how many leading / trailing cells of diagonal d can only hold one background state (see
+// StartEndConstraint); 0 / 0 for constraints that cannot tell.
 struct NoConstraint {
   RDEV bool ok(const ModelView&, const SeqView&, const Emit&) const { return true; }
+  RDEV void outside_cells(int, int, int& nb, int& na) const { nb = 0; na = 0; }
 };
 // motif start fixed at Ys (InsideEndFun, motif_scanner.hpp:606-639; mirrored in OutsideEndFun :720-760)
 struct StartConstraint {
   int ys;
+  RDEV void outside_cells(int, int, int& nb, int& na) const { nb = 0; na = 0; }
   RDEV bool ok(const ModelView& m, const SeqView&, const Emit& e) const {
     if (e.kind == 0) return true;
     const DevHMM& h = m.h;
@@ -278,6 +282,20 @@ struct StartConstraint {
 // motif start and end fixed (CYKFun, motif_scanner.hpp:843-880); ys = ye = -1 switches it off
 struct StartEndConstraint {
   int ys, ye;
+  // The node chain is monotone along the sequence and the vetoes below force the 0 -> 1 step onto position ys and the
+  // M-2 -> M-1 step onto position ye.  A cell whose bases all lie before ys can therefore appear in a complete parse
+  // only in state (0,0), one whose bases all lie after ye only in state (M-1,M-1); any other state of such a cell is
+  // finite on its own but every parent that uses it runs into a veto.  The Viterbi pass skips those states (they are
+  // stored as -inf): the root values, the arg-max path and its tie-breaking are unchanged, the work drops by ~S for
+  // every cell outside the motif.  Margins of one position keep clear of the emission conventions at ys / ye.
+  // cells of diagonal d are i = 0 .. ncell-1 with bases i .. i+d-1:  leading  i + d < ys,  trailing  i > ye + 1.
+  RDEV void outside_cells(int d, int ncell, int& nb, int& na) const {
+    nb = 0; na = 0;
+    if (ys < 0 || ye < ys || d == 0) return;
+    nb = ys - d; nb = nb < 0 ? 0 : (nb > ncell ? ncell : nb);
+    na = ncell - (ye + 2); na = na < 0 ? 0 : na;
+    if (na > ncell - nb) na = ncell - nb;
+  }
   RDEV bool ok(const ModelView& m, const SeqView& q, const Emit& e) const {
     if (e.kind == 0) return true;
     const DevHMM& h = m.h;

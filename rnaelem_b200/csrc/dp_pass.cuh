@@ -325,10 +325,37 @@ RDEV void cta_inside(const ModelView& m, const SeqView& q, double* tab, double* 
                      unsigned long long* otrace, CON con) {
   const int S = q.S, L = q.L, W = q.W;
   const DevHMM& h = m.h;
+  // background states of cells outside the motif (Viterbi with a fixed motif region only, see StartEndConstraint)
+  int s_bg0 = h.s00, s_bgM = -1;
+  if (MAXMODE)
+    for (int s = 0; s < S; ++s)
+      if (ld_ro(h.st_l + s) == h.M - 1 && ld_ro(h.st_r + s) == h.M - 1) s_bgM = s;
   for (int d = 0; d <= W; ++d) {
     int ncell = L + 1 - d;
-    for (int t = CTA_TID; t < ncell * S; t += CTA_NTH) {
-      int i = t / S, s = t - i * S;
+    int nb = 0, na = 0;
+    if (MAXMODE && s_bg0 >= 0 && s_bgM >= 0) con.outside_cells(d, ncell, nb, na);
+    // states that cannot be part of a complete parse: -inf, no enumeration
+    for (int t = CTA_TID; t < (nb + na) * S; t += CTA_NTH) {
+      int c = t / S, s = t - c * S;
+      int i = c < nb ? c : ncell - na + (c - nb);
+      if (s == (c < nb ? s_bg0 : s_bgM)) continue;
+      tab[band_idx(q, PL_L, i, d, s)] = NINF; trace[band_idx(q, PL_L, i, d, s)] = RELEM_NO_TRACE;
+      if (ok_P(q, i, d)) { tab[band_idx(q, PL_P, i, d, s)] = NINF; trace[band_idx(q, PL_P, i, d, s)] = RELEM_NO_TRACE; }
+      if (ok_B(q, i, d)) {
+        tab[band_idx(q, PL_B, i, d, s)] = NINF; trace[band_idx(q, PL_B, i, d, s)] = RELEM_NO_TRACE;
+        tab[band_idx(q, PL_2, i, d, s)] = NINF; trace[band_idx(q, PL_2, i, d, s)] = RELEM_NO_TRACE;
+        tab[band_idx(q, PL_1, i, d, s)] = NINF; trace[band_idx(q, PL_1, i, d, s)] = RELEM_NO_TRACE;
+      }
+      if (ok_M(q, i, d)) { tab[band_idx(q, PL_M, i, d, s)] = NINF; trace[band_idx(q, PL_M, i, d, s)] = RELEM_NO_TRACE; }
+      if (ok_E(q, i, d)) { tab[band_idx(q, PL_E, i, d, s)] = NINF; trace[band_idx(q, PL_E, i, d, s)] = RELEM_NO_TRACE; }
+    }
+    // everything else, compacted so that all lanes carry an enumeration: one state for each outside cell, S for the rest
+    const int nwork = nb + na + (ncell - nb - na) * S;
+    for (int t = CTA_TID; t < nwork; t += CTA_NTH) {
+      int i, s;
+      if (t < nb) { i = t; s = s_bg0; }
+      else if (t < nb + na) { i = ncell - na + (t - nb); s = s_bgM; }
+      else { int u = t - nb - na; i = nb + u / S; s = u - (u / S) * S; }
       // ---- L
       {
         unsigned idx = band_idx(q, PL_L, i, d, s);
@@ -368,7 +395,7 @@ RDEV void cta_inside(const ModelView& m, const SeqView& q, double* tab, double* 
       if (gM) RELEM_RUN(PL_M, enum_M)
       if (gE) RELEM_RUN(PL_E, enum_E)
 #undef RELEM_RUN
-    }
+        }
     CTA_SYNC();
   }
   // exterior recurrence
