@@ -101,6 +101,8 @@ struct LinKArgs {
   int base, count;   // this chunk handles sequences order[base .. base+count), slot k <-> sequence base+k
   int d;             // diagonal of a phase kernel
   int tile, ntile;   // cells per CTA and CTAs per sequence of a phase kernel
+  int win;           // 1: inside phase of the scanner's start-constrained pass -- tiles cover only the cells that
+                     //    contain position Ys (all other cells keep the values of the unconstrained pass)
   LinLayout lay;
   double* scratch;
   const double* k0pow;
@@ -294,8 +296,23 @@ LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 7)) relem_lin_phase_kernel(LinKAr
   const int d = a.d;
   if (d > q.W) return;
   const int ncell = q.L + 1 - d;
-  const int i0 = tk * a.tile, i1 = ncell < i0 + a.tile ? ncell : i0 + a.tile;
-  if (i0 >= ncell) return;
+  int i0 = tk * a.tile, i1 = ncell < i0 + a.tile ? ncell : i0 + a.tile;
+  // Scanner, second (start-constrained) pass.  The constraint vetoes emissions AT position Ys only, so
+  //  * inside: a cell that does not contain Ys has bit for bit the value the unconstrained pass left in the table;
+  //    only cells with i <= Ys < i+d are recomputed (one position of margin on either side);
+  //  * outside (MODE 2 collects end posteriors only): a cell whose bases all lie before Ys can neither emit a motif
+  //    end nor be read by a cell that can -- readers of an outside value are sub-cells -- so it is skipped.
+  if (PH >= PH_IN_L && PH <= PH_IN_E && a.win) {
+    const int ys = c.ys;
+    const int lo = ys - d > 0 ? ys - d : 0, hi = ys + 1 < ncell - 1 ? ys + 1 : ncell - 1;
+    i0 = lo + tk * a.tile;
+    i1 = hi + 1 < i0 + a.tile ? hi + 1 : i0 + a.tile;
+  }
+  if (PH >= PH_OUT_EM && MODE == 2) {
+    const int lo = c.ys - 1 - d;
+    if (i0 < lo) i0 = lo;
+  }
+  if (i0 >= i1) return;
   const int w0 = warp_id(), nw = n_warps();
   if (PH == PH_K0_IN || PH == PH_K0_OUT) {
     K0Tabs t0 = lin_k0tabs(lay, slot, a.k0pow + a.kp_n);
@@ -702,8 +719,19 @@ template <int PH, int NCH> static void launch_phase(Runner& r, int d, int tile, 
   if (ncell_max <= 0) return;
   if (tile > ncell_max) tile = ncell_max;
   tile = fit_tile(r, tile, ncell_max);
-  r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile;
+  r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile; r.a.win = 0;
   LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, NCH>), r.a.count * r.a.ntile, LIN_THREADS, smem);
+}
+
+// inside phase of the scanner's second pass: at most d + 2 cells per sequence contain Ys (see the kernel)
+template <int PH> static void launch_phase_win(Runner& r, int d, int tile, int smem) {
+  int ncell_max = r.a.lay.Lmax + 1 - d;
+  if (ncell_max <= 0) return;
+  if (ncell_max > d + 2) ncell_max = d + 2;
+  if (tile > ncell_max) tile = ncell_max;
+  tile = fit_tile(r, tile, ncell_max);
+  r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile; r.a.win = 1;
+  LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, 1>), r.a.count * r.a.ntile, LIN_THREADS, smem);
 }
 
 template <int PH, int MODE> static void launch_phase3(Runner& r, int d, int tile, int smem) {
@@ -711,7 +739,7 @@ template <int PH, int MODE> static void launch_phase3(Runner& r, int d, int tile
   if (ncell_max <= 0) return;
   if (tile > ncell_max) tile = ncell_max;
   tile = fit_tile(r, tile, ncell_max);
-  r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile;
+  r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile; r.a.win = 0;
   LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, 1, MODE>), r.a.count * r.a.ntile, LIN_THREADS, smem);
 }
 
@@ -760,12 +788,21 @@ static void run_chunk_scan(Runner& r, bool filter, int NT) {
   }
   for (int pass = 1; pass <= 2; ++pass) {
     for (int d = 0; d <= W; ++d) {
-      launch_phase<PH_IN_L, 1>(r, d, r.tile_d, r.smem_in);
-      if (d >= 5) {
-        launch_phase<PH_IN_P, 1>(r, d, r.tile_p, r.smem_in);
-        launch_phase<PH_IN_B, 1>(r, d, r.tile_d, r.smem_in);
+      if (pass == 1) {
+        launch_phase<PH_IN_L, 1>(r, d, r.tile_d, r.smem_in);
+        if (d >= 5) {
+          launch_phase<PH_IN_P, 1>(r, d, r.tile_p, r.smem_in);
+          launch_phase<PH_IN_B, 1>(r, d, r.tile_d, r.smem_in);
+        }
+        if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, r.tile_e, r.smem_in);
+      } else {
+        launch_phase_win<PH_IN_L>(r, d, r.tile_d, r.smem_in);
+        if (d >= 5) {
+          launch_phase_win<PH_IN_P>(r, d, r.tile_p, r.smem_in);
+          launch_phase_win<PH_IN_B>(r, d, r.tile_d, r.smem_in);
+        }
+        if (d >= 3) launch_phase_win<PH_IN_E>(r, d, r.tile_e, r.smem_in);
       }
-      if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, r.tile_e, r.smem_in);
     }
     if (pass == 1) {
       LIN_LAUNCH(r, (relem_lin_ext_kernel<2, 1, 1>), cnt, 32, r.smem_ext_in);

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Times the shipped RNAelem (B200) and the reference binary on the same FASTQ / command line and diffs the outputs.
-# usage: tools/cli_compare.sh NSEQ ITER BATCH OUTDIR
+# usage: [SKIP_REF=1] [GPUS=n] tools/cli_compare.sh NSEQ ITER BATCH OUTDIR
 set -e
 N=${1:-256}; IT=${2:-5}; B=${3:-100}; OUT=${4:-gpurun_out/cli}
 mkdir -p $OUT
@@ -15,11 +15,11 @@ with open(path, "w") as f:
 PY
 T=$(nproc)
 t0=$(date +%s.%N)
-rnaelem_b200/RNAelem -f $OUT/in.fq -m "((.*.))" --max-iter $IT --batch-size $B --lambda-init 1.5 \
+rnaelem_b200/RNAelem -f $OUT/in.fq -m "((.*.))" --max-iter $IT --batch-size $B --lambda-init 1.5 --gpus ${GPUS:-1} \
    --out1 $OUT/ours.model --out2 $OUT/ours.raw --out3 $OUT/ours.interim 2> $OUT/ours.err
 echo "ours: $(python -c "import sys,time; print(round(time.time()-float(sys.argv[1]),2))" $t0) s wall (whole command: train $IT evaluations of $B reads + model + scan of $N reads)"
 tail -4 $OUT/ours.err | cut -c1-200
-if [ -x oracle/_ref/RNAelem ]; then
+if [ -x oracle/_ref/RNAelem ] && [ -z "$SKIP_REF" ]; then
 t0=$(date +%s.%N)
 oracle/_ref/RNAelem -f $OUT/in.fq -m "((.*.))" -t $T --max-iter $IT --batch-size $B --lambda-init 1.5 \
    --out1 $OUT/ref.model --out2 $OUT/ref.raw --out3 $OUT/ref.interim 2> $OUT/ref.err
