@@ -233,7 +233,7 @@ RELEM_KERNEL relem_estep_kernel(ModelView nullm, ModelView m, BatchView b, SlotL
     }
     if (skip) {
       for (int t = CTA_TID; t < NT; t += CTA_NTH) { out.ENo[(long long)n * NT + t] = 0.; out.ENx[(long long)n * NT + t] = 0.; }
-      if (CTA_TID < 4) out.EH[n * 4 + CTA_TID] = 0.;
+      for (int t = CTA_TID; t < 4; t += CTA_NTH) out.EH[n * 4 + t] = 0.;
       CTA_SYNC();
       continue;
     }

@@ -1474,7 +1474,11 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
 }
 
 // ---- outside, phase L (every cell): hairpin E(i,j,s) <- L(i,j,s); parent L(i,j+1,sp) emitting x[j]; unpaired flanks
-template <int NCH, int MODE = 0>
+// PART 0: everything in one call.  The wavefront launches it as three kernels -- PART 1 (hairpin + parent L, stores
+// bL), PART 2 (left flanks, adds to bL), PART 3 (right flanks, adds to bL) -- because the fused body is ~4 400 SASS
+// instructions (70 KB) against a 32 KB instruction cache and a third of its stall cycles were instruction fetch.  The
+// order of the floating-point additions is the same either way.
+template <int NCH, int MODE = 0, int PART = 0>
 RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, WarpLin& w, EhAcc<NCH>& eh) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
@@ -1483,7 +1487,13 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
   const bool ne = LC.en.no_ene != 0;
   const unsigned il = cidx(q, i, d);
   double* cL = w.curB;  // [NCH][S]
-  {
+  if (PART >= 2) {
+    if (!(d >= 1 && d <= c.Ceff && h.n_quad > 0)) return;
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) cL[ch * S + s] = 0.;
+    w_sync();
+  }
+  if (PART <= 1) {
     bool cH = gE;
     double tH = 0., h0 = 1., h1 = 1.;
     if (gE && !ne) {
@@ -1506,7 +1516,7 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
     }
     w_sync();
   }
-  if (d + 1 <= W && j + 1 <= L) {
+  if (PART <= 1 && d + 1 <= W && j + 1 <= L) {
     const int xr = q.x[j];
     const double wsr = c.wsf[j];
     const unsigned pb = cidx(q, i, d + 1);
@@ -1533,8 +1543,9 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
       for (int ch = 0; ch < NCH; ++ch) cL[ch * S + s] += seg_sum(w.partA + ch * NM, h.rT_off, s);
     w_sync();
   }
-  if (d >= 1 && d <= c.Ceff && h.n_quad > 0) {
-    if (i >= 1) {
+  bool touched = false;
+  if (PART != 1 && d >= 1 && d <= c.Ceff && h.n_quad > 0) {
+    if (PART != 3 && i >= 1) {
       const unsigned eb = cidx(q, i, 0);
       bool any = false;
       walk_left_flank(c, i, d, w, [&](int n) {
@@ -1561,9 +1572,10 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
       if (any)
         for (int s = lane; s < S; s += WARP_N)
           for (int ch = 0; ch < NCH; ++ch) cL[ch * S + s] += seg_sum(w.partA + ch * NM, h.qL_off, s);
+      touched = touched || any;
       w_sync();
     }
-    if (j + 1 <= L) {
+    if (PART != 2 && j + 1 <= L) {
       const unsigned eb = cidx(q, j, 0);
       bool any = false;
       walk_right_flank(c, i, d, w, [&](int n) {
@@ -1590,12 +1602,18 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
       if (any)
         for (int s = lane; s < S; s += WARP_N)
           for (int ch = 0; ch < NCH; ++ch) cL[ch * S + s] += seg_sum(w.partA + ch * NM, h.qR_off, s);
+      touched = touched || any;
       w_sync();
     }
   }
-  if (d >= 1)
+  if (PART >= 2) {
+    if (touched)
+      for (int s = lane; s < S; s += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) t.bL[ch * t.bch + il + s] += cL[ch * S + s];
+  } else if (d >= 1) {
     for (int s = lane; s < S; s += WARP_N)
       for (int ch = 0; ch < NCH; ++ch) t.bL[ch * t.bch + il + s] = cL[ch * S + s];
+  }
   w_sync();
 }
 

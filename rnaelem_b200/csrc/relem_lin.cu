@@ -251,7 +251,8 @@ LIN_KERNEL(LIN_THREADS, 8) relem_lin_prep_kernel(LinKArgs a LIN_SMEM_ARG) {
 }
 
 // ------------------------------------------------------------------------------------------------ phases
-enum { PH_K0_IN = 0, PH_K0_OUT, PH_IN_L, PH_IN_P, PH_IN_B, PH_IN_E, PH_OUT_EM, PH_OUT_B, PH_OUT_P, PH_OUT_L };
+enum { PH_K0_IN = 0, PH_K0_OUT, PH_IN_L, PH_IN_P, PH_IN_B, PH_IN_E, PH_OUT_EM, PH_OUT_B, PH_OUT_P, PH_OUT_L,
+       PH_OUT_LF, PH_OUT_LR };   // LF / LR: left / right flank gathers of outside L as kernels of their own
 
 // posterior sums of the CTA -> the sequence's accumulators in its slot header
 template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot, WarpLin& w, EhAcc<NCH>& eh) {
@@ -355,9 +356,11 @@ LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 7)) relem_lin_phase_kernel(LinKAr
       }
       if (PH == PH_OUT_B) { if (ok_B(q, i, d)) lin_out_B<NCH, MODE>(c, t, i, d, ok_M(q, i, d), w); }
       if (PH == PH_OUT_P) { if (ok_P(q, i, d)) lin_out_P<NCH, MODE>(c, t, i, d, ok_B(q, i, d), w, eh); }
-      if (PH == PH_OUT_L) lin_out_L<NCH, MODE>(c, t, i, d, d >= 3 && ok_E(q, i, d), w, eh);
+      if (PH == PH_OUT_L) lin_out_L<NCH, MODE, 1>(c, t, i, d, d >= 3 && ok_E(q, i, d), w, eh);
+      if (PH == PH_OUT_LF) lin_out_L<NCH, MODE, 2>(c, t, i, d, false, w, eh);
+      if (PH == PH_OUT_LR) lin_out_L<NCH, MODE, 3>(c, t, i, d, false, w, eh);
     }
-    lin_flush_counts<NCH>(lay, slot, w, eh);
+    if (PH != PH_OUT_LF && PH != PH_OUT_LR) lin_flush_counts<NCH>(lay, slot, w, eh);
   }
 }
 
@@ -680,6 +683,7 @@ struct Runner {
   int smem_in, smem_out, smem_small, smem_k0, smem_ext_in, smem_ext_out;
   int launches = 0;
   int resident_ctas = 148 * 7;
+  int cmax = 30;                   // longest unpaired flank of an interior loop: min(30, max_iloop, W - 7)
   int fill = 4;                    // CTAs per resident slot a small launch aims for (RELEM_FILL)
   int tile_p = 128, tile_e = 256;   // cells per CTA of the phases that touch few cells
   int tile_k0 = 32, tile_d = 64;   // cells per CTA of the dense phases (measured sweet spot, RELEM_TILE_*)
@@ -770,6 +774,10 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
       launch_phase<PH_OUT_P, NCH>(r, d, r.tile_e, r.smem_out);
     }
     launch_phase<PH_OUT_L, NCH>(r, d, r.tile_d, r.smem_out);
+    if (d >= 1 && d <= r.cmax) {
+      launch_phase<PH_OUT_LF, NCH>(r, d, r.tile_d, r.smem_out);
+      launch_phase<PH_OUT_LR, NCH>(r, d, r.tile_d, r.smem_out);
+    }
   }
   LIN_LAUNCH(r, (relem_lin_fold_kernel<NCH>), cnt, LIN_THREADS, NCH * NT * 8 + 16);
 }
@@ -819,6 +827,10 @@ static void run_chunk_scan(Runner& r, bool filter, int NT) {
           launch_phase3<PH_OUT_P, 1>(r, d, r.tile_e, r.smem_out);
         }
         launch_phase3<PH_OUT_L, 1>(r, d, r.tile_d, r.smem_out);
+        if (d >= 1 && d <= r.cmax) {
+          launch_phase3<PH_OUT_LF, 1>(r, d, r.tile_d, r.smem_out);
+          launch_phase3<PH_OUT_LR, 1>(r, d, r.tile_d, r.smem_out);
+        }
       } else {
         if (d >= 3) launch_phase3<PH_OUT_EM, 2>(r, d, r.tile_p, r.smem_out);
         if (d >= 5) {
@@ -826,6 +838,10 @@ static void run_chunk_scan(Runner& r, bool filter, int NT) {
           launch_phase3<PH_OUT_P, 2>(r, d, r.tile_e, r.smem_out);
         }
         launch_phase3<PH_OUT_L, 2>(r, d, r.tile_d, r.smem_out);
+        if (d >= 1 && d <= r.cmax) {
+          launch_phase3<PH_OUT_LF, 2>(r, d, r.tile_d, r.smem_out);
+          launch_phase3<PH_OUT_LR, 2>(r, d, r.tile_d, r.smem_out);
+        }
       }
     }
     if (pass == 1) LIN_LAUNCH(r, (relem_lin_scanfold_kernel<1>), cnt, LIN_THREADS, NT * 8 + 16);
@@ -850,6 +866,7 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   r.smem_out = lay.sm_warp + LIN_WARPS * lay.warp_bytes_out;
   r.smem_ext_in = lay.sm_warp + lay.warp_bytes_in;
   r.smem_ext_out = lay.sm_warp + lay.warp_bytes_out;
+  r.cmax = std::min(30, std::min((int)in.en.max_iloop, lay.Wmax - 7));
   const int NT = in.p.n_theta;
   if (const char* e = std::getenv("RELEM_FILL")) r.fill = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("RELEM_TILE_K0")) r.tile_k0 = std::max(4, std::atoi(e));
@@ -989,6 +1006,7 @@ int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_ch
   r.smem_out = lay.sm_warp + LIN_WARPS * lay.warp_bytes_out;
   r.smem_ext_in = lay.sm_warp + lay.warp_bytes_in;
   r.smem_ext_out = lay.sm_warp + lay.warp_bytes_out;
+  r.cmax = std::min(30, std::min((int)in.en.max_iloop, lay.Wmax - 7));
   const int NT = in.p.n_theta;
   const int KP = std::max(256, (lay.Wmax + 3 + 31) & ~31);
   std::vector<double> kp(KP + 1024, 0.);
