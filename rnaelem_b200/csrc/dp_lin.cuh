@@ -1329,7 +1329,9 @@ template <int NCH, int MODE = 0> RDEV void lin_out_B(const LinCtx& c, const CTab
 }
 
 // ---- outside, phase P (cells with an allowed pair)
-template <int NCH, int MODE = 0>
+// PART 0: everything.  The wavefront launches PART 1 (2 <- P, stacking parent, exterior parent; stores bP) and PART 2
+// (enclosing interior loops; adds to bP) as separate kernels for the same instruction-cache reason as lin_out_L.
+template <int NCH, int MODE = 0, int PART = 0>
 RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, WarpLin& w, EhAcc<NCH>& eh) {
   const LinHMM& h = LC.h;
   const LinParams& p = LC.p;
@@ -1338,8 +1340,14 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
   const bool ne = LC.en.no_ene != 0;
   const unsigned il = cidx(q, i, d), ir = cidx(q, j, d);
   double* cP = w.curB;  // [NCH][S]
+  if (PART == 2) {
+    if (h.n_quad <= 0) return;
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) cP[ch * S + s] = 0.;
+    w_sync();
+  }
   // 2(i,j,s) <- P(i,j,s)
-  {
+  if (PART <= 1) {
     bool c2P = gB;
     double tsc = 0., f0 = 1., f1 = 1.;
     if (gB && !ne) {
@@ -1362,7 +1370,7 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
     w_sync();
   }
   // parent P(i-1,j+1,s) stacking on this pair
-  if (ok_P(q, i - 1, d + 2)) {
+  if (PART <= 1 && ok_P(q, i - 1, d + 2)) {
     bool cPP = true;
     double tsc = 0., f0 = 1., f1 = 1.;
     if (!ne) {
@@ -1402,7 +1410,7 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
     }
   }
   // exterior parent O(j,s) <- O(i,sl) P(i,j,sr)
-  {
+  if (PART <= 1) {
     bool cX = true;
     double tsc = 0., f0 = 1., f1 = 1.;
     if (!ne) {
@@ -1433,7 +1441,7 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
     }
   }
   // enclosing interior loops E(i',j',s) <- P(i,j,s1) L(i',i,s2) L(j,j',s3)
-  if (h.n_quad > 0) {
+  if (PART != 1 && h.n_quad > 0) {
     for (int a = lane; a < h.n_quad; a += WARP_N)
       for (int ch = 0; ch < NCH; ++ch) { w.partA[ch * NM + a] = 0.; w.partT[ch * NM + a] = 0.; }
     w_sync();
@@ -1468,8 +1476,13 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
       for (int ch = 0; ch < NCH; ++ch) cP[ch * S + s] += seg_sum(w.partA + ch * NM, h.qP_off, s);
     w_sync();
   }
-  for (int s = lane; s < S; s += WARP_N)
-    for (int ch = 0; ch < NCH; ++ch) t.bP[ch * t.bch + il + s] = cP[ch * S + s];
+  if (PART == 2) {
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) t.bP[ch * t.bch + il + s] += cP[ch * S + s];
+  } else {
+    for (int s = lane; s < S; s += WARP_N)
+      for (int ch = 0; ch < NCH; ++ch) t.bP[ch * t.bch + il + s] = cP[ch * S + s];
+  }
   w_sync();
 }
 

@@ -252,7 +252,8 @@ LIN_KERNEL(LIN_THREADS, 8) relem_lin_prep_kernel(LinKArgs a LIN_SMEM_ARG) {
 
 // ------------------------------------------------------------------------------------------------ phases
 enum { PH_K0_IN = 0, PH_K0_OUT, PH_IN_L, PH_IN_P, PH_IN_B, PH_IN_E, PH_OUT_EM, PH_OUT_B, PH_OUT_P, PH_OUT_L,
-       PH_OUT_LF, PH_OUT_LR };   // LF / LR: left / right flank gathers of outside L as kernels of their own
+       PH_OUT_LF, PH_OUT_LR,     // LF / LR: left / right flank gathers of outside L as kernels of their own
+       PH_OUT_PQ };              // enclosing interior loops of outside P
 
 // posterior sums of the CTA -> the sequence's accumulators in its slot header
 template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot, WarpLin& w, EhAcc<NCH>& eh) {
@@ -355,7 +356,8 @@ LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 7)) relem_lin_phase_kernel(LinKAr
         if (gE || gM) lin_out_EM<NCH, MODE>(c, t, i, d, gE, gM, w, eh);
       }
       if (PH == PH_OUT_B) { if (ok_B(q, i, d)) lin_out_B<NCH, MODE>(c, t, i, d, ok_M(q, i, d), w); }
-      if (PH == PH_OUT_P) { if (ok_P(q, i, d)) lin_out_P<NCH, MODE>(c, t, i, d, ok_B(q, i, d), w, eh); }
+      if (PH == PH_OUT_P) { if (ok_P(q, i, d)) lin_out_P<NCH, MODE, 1>(c, t, i, d, ok_B(q, i, d), w, eh); }
+      if (PH == PH_OUT_PQ) { if (ok_P(q, i, d)) lin_out_P<NCH, MODE, 2>(c, t, i, d, false, w, eh); }
       if (PH == PH_OUT_L) lin_out_L<NCH, MODE, 1>(c, t, i, d, d >= 3 && ok_E(q, i, d), w, eh);
       if (PH == PH_OUT_LF) lin_out_L<NCH, MODE, 2>(c, t, i, d, false, w, eh);
       if (PH == PH_OUT_LR) lin_out_L<NCH, MODE, 3>(c, t, i, d, false, w, eh);
@@ -772,6 +774,7 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
     if (d >= 5) {
       launch_phase<PH_OUT_B, NCH>(r, d, r.tile_d, r.smem_out);
       launch_phase<PH_OUT_P, NCH>(r, d, r.tile_e, r.smem_out);
+      launch_phase<PH_OUT_PQ, NCH>(r, d, r.tile_e, r.smem_out);
     }
     launch_phase<PH_OUT_L, NCH>(r, d, r.tile_d, r.smem_out);
     if (d >= 1 && d <= r.cmax) {
@@ -825,6 +828,7 @@ static void run_chunk_scan(Runner& r, bool filter, int NT) {
         if (d >= 5) {
           launch_phase3<PH_OUT_B, 1>(r, d, r.tile_d, r.smem_out);
           launch_phase3<PH_OUT_P, 1>(r, d, r.tile_e, r.smem_out);
+          launch_phase3<PH_OUT_PQ, 1>(r, d, r.tile_e, r.smem_out);
         }
         launch_phase3<PH_OUT_L, 1>(r, d, r.tile_d, r.smem_out);
         if (d >= 1 && d <= r.cmax) {
@@ -836,6 +840,7 @@ static void run_chunk_scan(Runner& r, bool filter, int NT) {
         if (d >= 5) {
           launch_phase3<PH_OUT_B, 2>(r, d, r.tile_d, r.smem_out);
           launch_phase3<PH_OUT_P, 2>(r, d, r.tile_e, r.smem_out);
+          launch_phase3<PH_OUT_PQ, 2>(r, d, r.tile_e, r.smem_out);
         }
         launch_phase3<PH_OUT_L, 2>(r, d, r.tile_d, r.smem_out);
         if (d >= 1 && d <= r.cmax) {
