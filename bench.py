@@ -11,7 +11,7 @@ N > 1 the NCCL all-reduce of those P+3 doubles.
 metric  dp_cells_per_s = band cells x 3 coupled passes (inside + 2 outside, the reference's pass count) per second,
         whole job.  `value`: batch resident in HBM.  `e2e`: the host-buffer entry point relem_estep (H2D of the
         batch from pinned memory and D2H of the result inside the timed region).
-roofline  the E-step is one wavefront of small kernels (relem_lin_phase_kernel<phase> per span and phase, 486 launches
+roofline  the E-step is one wavefront of small kernels (relem_lin_phase_kernel<phase> per span and phase, 592 launches
         per chunk of sequences); `achieved` = algorithmic bytes (cells x 168 x S) / summed device time of
         those launches (CUDA events on the launch stream) against the measured HBM copy bandwidth; `traffic` = measured
         DRAM bytes of the same launches (ncu dram__bytes_read+write, profiles/r1_dram_traffic.json) scaled to the batch.

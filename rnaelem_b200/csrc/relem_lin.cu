@@ -281,8 +281,14 @@ template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot
 
 // grid = count * ntile CTAs; CTA (sk, tk) owns cells [tk*tile, (tk+1)*tile) of diagonal d of sequence slot sk,
 // its warps take them interleaved
+// resident CTAs per SM the register allocation aims at: 8 for the energy-only phases (62 registers), 7 (72 registers)
+// for the coupled ones; LIN_MINB_SPLIT lets an experiment build the split-gather phases (memory-latency bound) at 8
+#ifndef LIN_MINB_SPLIT
+#define LIN_MINB_SPLIT 7
+#endif
 template <int PH, int NCH, int MODE = 0>
-LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : 7)) relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
+LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : (PH == PH_OUT_B || PH == PH_IN_B) ? LIN_MINB_SPLIT : 7))
+relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
@@ -689,6 +695,7 @@ struct Runner {
   int fill = 4;                    // CTAs per resident slot a small launch aims for (RELEM_FILL)
   int tile_p = 128, tile_e = 256;   // cells per CTA of the phases that touch few cells
   int tile_k0 = 32, tile_d = 64;   // cells per CTA of the dense phases (measured sweet spot, RELEM_TILE_*)
+  int tile_f = 64, tile_q = 256;   // flank kernels of outside L, interior-loop kernel of outside P
 #ifdef RELEM_HOST_EMU
   std::vector<unsigned char> smem;
 #else
@@ -774,12 +781,12 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
     if (d >= 5) {
       launch_phase<PH_OUT_B, NCH>(r, d, r.tile_d, r.smem_out);
       launch_phase<PH_OUT_P, NCH>(r, d, r.tile_e, r.smem_out);
-      launch_phase<PH_OUT_PQ, NCH>(r, d, r.tile_e, r.smem_out);
+      launch_phase<PH_OUT_PQ, NCH>(r, d, r.tile_q, r.smem_out);
     }
     launch_phase<PH_OUT_L, NCH>(r, d, r.tile_d, r.smem_out);
     if (d >= 1 && d <= r.cmax) {
-      launch_phase<PH_OUT_LF, NCH>(r, d, r.tile_d, r.smem_out);
-      launch_phase<PH_OUT_LR, NCH>(r, d, r.tile_d, r.smem_out);
+      launch_phase<PH_OUT_LF, NCH>(r, d, r.tile_f, r.smem_out);
+      launch_phase<PH_OUT_LR, NCH>(r, d, r.tile_f, r.smem_out);
     }
   }
   LIN_LAUNCH(r, (relem_lin_fold_kernel<NCH>), cnt, LIN_THREADS, NCH * NT * 8 + 16);
@@ -828,24 +835,24 @@ static void run_chunk_scan(Runner& r, bool filter, int NT) {
         if (d >= 5) {
           launch_phase3<PH_OUT_B, 1>(r, d, r.tile_d, r.smem_out);
           launch_phase3<PH_OUT_P, 1>(r, d, r.tile_e, r.smem_out);
-          launch_phase3<PH_OUT_PQ, 1>(r, d, r.tile_e, r.smem_out);
+          launch_phase3<PH_OUT_PQ, 1>(r, d, r.tile_q, r.smem_out);
         }
         launch_phase3<PH_OUT_L, 1>(r, d, r.tile_d, r.smem_out);
         if (d >= 1 && d <= r.cmax) {
-          launch_phase3<PH_OUT_LF, 1>(r, d, r.tile_d, r.smem_out);
-          launch_phase3<PH_OUT_LR, 1>(r, d, r.tile_d, r.smem_out);
+          launch_phase3<PH_OUT_LF, 1>(r, d, r.tile_f, r.smem_out);
+          launch_phase3<PH_OUT_LR, 1>(r, d, r.tile_f, r.smem_out);
         }
       } else {
         if (d >= 3) launch_phase3<PH_OUT_EM, 2>(r, d, r.tile_p, r.smem_out);
         if (d >= 5) {
           launch_phase3<PH_OUT_B, 2>(r, d, r.tile_d, r.smem_out);
           launch_phase3<PH_OUT_P, 2>(r, d, r.tile_e, r.smem_out);
-          launch_phase3<PH_OUT_PQ, 2>(r, d, r.tile_e, r.smem_out);
+          launch_phase3<PH_OUT_PQ, 2>(r, d, r.tile_q, r.smem_out);
         }
         launch_phase3<PH_OUT_L, 2>(r, d, r.tile_d, r.smem_out);
         if (d >= 1 && d <= r.cmax) {
-          launch_phase3<PH_OUT_LF, 2>(r, d, r.tile_d, r.smem_out);
-          launch_phase3<PH_OUT_LR, 2>(r, d, r.tile_d, r.smem_out);
+          launch_phase3<PH_OUT_LF, 2>(r, d, r.tile_f, r.smem_out);
+          launch_phase3<PH_OUT_LR, 2>(r, d, r.tile_f, r.smem_out);
         }
       }
     }
@@ -878,6 +885,8 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   if (const char* e = std::getenv("RELEM_TILE_D")) r.tile_d = std::max(4, std::atoi(e));
   if (const char* e = std::getenv("RELEM_TILE_P")) r.tile_p = std::max(4, std::atoi(e));
   if (const char* e = std::getenv("RELEM_TILE_E")) r.tile_e = std::max(4, std::atoi(e));
+  if (const char* e = std::getenv("RELEM_TILE_F")) r.tile_f = std::max(4, std::atoi(e));
+  if (const char* e = std::getenv("RELEM_TILE_Q")) r.tile_q = std::max(4, std::atoi(e));
   // kappa0 powers [0, KP) followed by the separable interior-loop table G[32][32]; the device fills G (gtab kernel)
   const int KP = std::max(256, (lay.Wmax + 3 + 31) & ~31);
   std::vector<double> kp(KP + 1024, 0.);
