@@ -71,3 +71,25 @@ def test_cli_two_gpus(product_cli, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     clilib.check_case(product_cli, "synth_adam", str(tmp_path), extra_args=["--gpus", "2"])
+
+
+def test_model_written_here_is_read_by_the_reference(emu_cli, tmp_path):
+    """drop-in in the other direction: a train.model written by this host layer must be accepted by the unmodified
+    reference binary, and both must then print the same scan records (same parameter bits -> exact Viterbi lines)"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "RNAelem")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/RNAelem not built")
+    fq = os.path.join(clilib.HERE, "golden", "_tmp", "trna.fq")
+    model = str(tmp_path / "ours.model")
+    p = subprocess.run([emu_cli, "-f", fq, "-m", "(.*.)", "--max-iter", "3", "--batch-size", "2", "--lambda-init", "0.7",
+                        "--out1", model, "--out2", str(tmp_path / "x.raw"), "--out3", str(tmp_path / "x.interim")],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    outs = {}
+    for name, binary in (("ref", ref), ("ours", emu_cli)):
+        raw = str(tmp_path / (name + ".raw"))
+        p = subprocess.run([binary, "scan", "-f", fq, "-q", model, "-t", "1", "--out1", raw], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        outs[name] = (open(raw).read(), p.stderr)
+    clilib.compare_text(outs["ref"][0], outs["ours"][0], "scan.raw with a model written here")
+    clilib.compare_text(outs["ref"][1], outs["ours"][1], "scan stderr")
