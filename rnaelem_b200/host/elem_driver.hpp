@@ -94,7 +94,8 @@ struct PackedBatch {
   std::vector<int32_t> gate;
   std::vector<std::string> id;
   int n() const { return int(kind.size()); }
-  void add(const VI& codes, const V& w, int kd, int g, const std::string& name) {
+  template <class Codes>
+  void add(const Codes& codes, const V& w, int kd, int g, const std::string& name) {
     for (int c : codes) seq.push_back(uint8_t(c));
     ws.insert(ws.end(), w.begin(), w.end());
     off.push_back(int64_t(seq.size()));

@@ -18,6 +18,7 @@
 #define RELEM_ELEM_HOST_HPP
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -113,16 +114,17 @@ inline int base_code(char c) {   // bio_sequence.hpp:30-41
     default: return 0;
   }
 }
-inline std::string codes_to_text(const VI& seq) {
+template <class Codes>
+std::string codes_to_text(const Codes& seq) {
   std::string s(seq.size(), 'N');
   for (size_t k = 0; k < seq.size(); ++k) s[k] = "NACGU"[seq[k]];
   return s;
 }
 
-struct Read {
-  std::string id;   // whole header line including '@'
-  VI seq;           // base codes 0..4
-  VI qual;          // quality values (char - 33), L+1 of them in RNAelem's FASTQ dialect
+struct Read {                  // ~3 bytes per base: a scan input of 10^6 x 200-nt reads stays well under 1 GB
+  std::string id;              // whole header line including '@'
+  std::vector<uint8_t> seq;    // base codes 0..4
+  std::vector<int16_t> qual;   // quality values (char - 33), L+1 of them in RNAelem's FASTQ dialect
 };
 
 // Strict 4-lines-per-record FASTQ (fastq_io.hpp:64-114).  A record counts only if the stream is still good after
@@ -150,9 +152,9 @@ class FastqReader {
       Read r;
       r.id = id;
       r.seq.resize(seq.size());
-      for (size_t k = 0; k < seq.size(); ++k) r.seq[k] = base_code(seq[k]);
+      for (size_t k = 0; k < seq.size(); ++k) r.seq[k] = uint8_t(base_code(seq[k]));
       r.qual.resize(qual.size());
-      for (size_t k = 0; k < qual.size(); ++k) r.qual[k] = int(qual[k]) - base;
+      for (size_t k = 0; k < qual.size(); ++k) r.qual[k] = int16_t(int(qual[k]) - base);
       rec_.push_back(std::move(r));
     }
     order_.resize(rec_.size());
@@ -201,7 +203,8 @@ class FastqBatchReader {
 // RNAelem::set_ws (motif_model.hpp:62-70): L+1 quality values -> L log position weights relative to the modal
 // quality (last maximum of the histogram, util.hpp:231-241) and the trailing "contains the motif" flag
 // (returned: true when the flag value is 0, i.e. the quality string ends in '!').
-inline bool quality_to_weights(const VI& q, V& ws) {
+template <class Quals>
+bool quality_to_weights(const Quals& q, V& ws) {
   VI hist(127 - 33, 0);
   for (int v : q) hist.at(v) += 1;
   int mode = 0, best = std::numeric_limits<int>::lowest();
