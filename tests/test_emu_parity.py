@@ -44,3 +44,29 @@ def test_no_rss_linear_model(emu_lib):
     sc, off, wc = rb.pack_batch(seqs, wss)
     with pytest.raises(rb.RelemError):
         ctx.bpp(ctx.batch(sc, off, wc))   # no base-pair filter in this mode
+
+
+def _lik_ratio_signs(lib):
+    """--lik-ratio kinds (include/relem.h): kinds 3 / 4 are the kind-1 terms with the opposite sign; 4 does not count
+    towards sum_eff (motif_trainer.hpp:156-202)"""
+    import numpy as np
+    case = caselib.load_case("ragged")
+    ctx = caselib.make_ctx(case, lib=lib)
+    seqs, wss = caselib.scan_inputs(case)
+    seqs, wss = seqs[3:], wss[3:]          # the reads long enough to hold the motif
+    sc, off, wc = rb.pack_batch(seqs, wss)
+    n = len(seqs)
+    res = {}
+    for kd in (rb.POS_WITH, rb.LR_WITHOUT, rb.LR_NEG):
+        res[kd] = ctx.estep_run(ctx.batch(sc, off, wc, np.full(n, kd, np.uint8), np.full(n, -1, np.int32)))
+    a, b, c = res[rb.POS_WITH], res[rb.LR_WITHOUT], res[rb.LR_NEG]
+    assert a.n_skipped == 0 and a.fn != 0.
+    for r in (b, c):
+        assert caselib.close(r.fn, -a.fn)
+        caselib.assert_close_vec(r.EN_diff, -np.asarray(a.EN_diff), "EN_diff sign")
+        caselib.assert_close_vec(r.EH_diff, -np.asarray(a.EH_diff), "EH_diff sign")
+    assert caselib.close(b.sum_eff, a.sum_eff) and c.sum_eff == 0.
+
+
+def test_lik_ratio_kinds(emu_lib):
+    _lik_ratio_signs(emu_lib)
