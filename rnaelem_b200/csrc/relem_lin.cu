@@ -282,12 +282,15 @@ template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot
 // grid = count * ntile CTAs; CTA (sk, tk) owns cells [tk*tile, (tk+1)*tile) of diagonal d of sequence slot sk,
 // its warps take them interleaved
 // resident CTAs per SM the register allocation aims at: 8 for the energy-only phases (62 registers), 7 (72 registers)
-// for the coupled ones; LIN_MINB_SPLIT lets an experiment build the split-gather phases (memory-latency bound) at 8
+// for the coupled ones, 8 (64 registers) for the split-gather phases, which are bound by memory latency
 #ifndef LIN_MINB_SPLIT
-#define LIN_MINB_SPLIT 7
+#define LIN_MINB_SPLIT 8   // measured: 9 314 -> 9 446 sequence-evaluations/s (64 registers, no spills)
+#endif
+#ifndef LIN_MINB_SMALL
+#define LIN_MINB_SMALL 7
 #endif
 template <int PH, int NCH, int MODE = 0>
-LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : (PH == PH_OUT_B || PH == PH_IN_B) ? LIN_MINB_SPLIT : 7))
+LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : (PH == PH_OUT_B || PH == PH_IN_B) ? LIN_MINB_SPLIT : (PH == PH_OUT_L || PH == PH_OUT_EM || PH == PH_IN_P || PH == PH_IN_L) ? LIN_MINB_SMALL : 7))
 relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
