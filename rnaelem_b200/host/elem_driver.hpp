@@ -148,6 +148,14 @@ class RNAelemTrainer {
 
   // the objective: fn = sum over the minibatch of ln Zo - ln Zx, gr = expected-count differences
   int operator()(const V& x, double& fn, V& gr) {
+    const bool prof = std::getenv("RELEM_HOST_PROFILE") != nullptr;   // stderr: host-side time per stage of this call
+    auto tp0 = std::chrono::steady_clock::now();
+    auto lapse = [&tp0] {
+      auto t = std::chrono::steady_clock::now();
+      double ms = std::chrono::duration<double, std::milli>(t - tp0).count();
+      tp0 = t;
+      return ms;
+    };
     if (qr_.size() - qr_.consumed_in_epoch() < qr_.batch_size()) qr_.skip(qr_.size() - qr_.consumed_in_epoch());
     motif_->unpack(x);
     if (qr_.epoch_done()) write_interim(out_, 3, *motif_);
@@ -185,7 +193,9 @@ class RNAelemTrainer {
       b.add(rs[i]->seq, wv[i], flagged[i] ? RELEM_POS_WITH : lr ? RELEM_LR_WITHOUT : RELEM_POS_WITHOUT, -1, rs[i]->id);
       b.add(negv[i], V(negv[i].size(), 0.), lr ? RELEM_LR_NEG : RELEM_NEG, me, rs[i]->id);   // qualities all 0 -> weight 0
     }
+    const double ms_pack = lapse();
     dev_.push_params(*motif_);
+    const double ms_push = lapse();
 
     const int nth = motif_->n_theta(), nw = dev_.size();
     V en(nth, 0.);
@@ -214,6 +224,14 @@ class RNAelemTrainer {
       v[3 + nth] = o.EH_diff[0]; v[4 + nth] = o.EH_diff[1];
       if (nw > 1) dev_.ok(k, relem_allreduce_sum(dev_.ctx(k), v.data(), int(v.size())), "relem_allreduce_sum");
     });
+    const double ms_estep = lapse();
+    if (prof) {
+      const char* nm[8]; float ms[8]; int nl[8];
+      int ne = relem_last_timing(dev_.ctx(0), nm, ms, nl, 8);
+      double kms = 0.;
+      for (int k = 0; k < ne; ++k) kms += ms[k];
+      cry("host profile: pack", ms_pack, "ms, set_params", ms_push, "ms, relem_estep", ms_estep, "ms of which kernels", kms, "ms");
+    }
     const V& tot = part[0];
     fn = tot[0]; sum_eff_ = tot[1];
     for (int k = 0; k < nth; ++k) en[k] = tot[3 + k];
