@@ -322,8 +322,8 @@ struct MotifModel {
     std::string r;
     for (char c : p) if (!(c == '*' && !r.empty() && r.back() == '*')) r += c;
     size_t a = r.find_first_not_of('*');
-    r.erase(0, a == std::string::npos ? 0 : a);   // an all-'*' pattern keeps its stars as in the reference's erase(0,npos)==all
-    if (a == std::string::npos) return std::string();
+    if (a == std::string::npos) return std::string();   // nothing but '*': the reference's erase(0, npos) leaves ""
+    r.erase(0, a);
     size_t b = r.find_last_not_of('*');
     if (b != std::string::npos) r.erase(b + 1);
     return r;

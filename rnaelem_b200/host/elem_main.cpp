@@ -6,6 +6,7 @@
 // One addition: --gpus N (or RELEM_GPUS) shards each minibatch / scan over N GPUs of the box.  `-t/--thread` is
 // accepted and ignored (the batch runs on the GPU).  Sub-commands that only exist for the reference's Grid Engine
 // fan-out or debugging (array-eval, eval, develop, logo) are refused.
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 
