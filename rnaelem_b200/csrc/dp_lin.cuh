@@ -805,24 +805,7 @@ RDEV void lin_in_B(const LinCtx& c, const CTabs& t, int i, int d, bool gP, bool 
     }
     const double* r1 = t.a1 + cidx(q, i, 0);
     const double* r2 = t.a2 + cidx(q, j, 0) + (unsigned)d * S;
-    // The list rarely fills its last round of 32 lanes (41 entries for ((.*.)): 9 of 32).  When at least two lanes are
-    // free per entry of that round, G = 32 / rem lanes share each entry, every G-th split point each, and their
-    // partial sums meet through shuffles.
-    const int nfull = (h.n_split / WARP_N) * WARP_N, rem = h.n_split - nfull;
-    const int G = rem > 0 ? WARP_N / rem : 1;
-    if (G >= 2) {
-      const int e = lane % rem, g = lane / rem;
-      double v = 0.;
-      if (g < G) {
-        const double* p1 = r1 + ld_ro(h.sp_l + nfull + e);
-        const double* p2 = r2 + ld_ro(h.sp_r + nfull + e);
-        for (int tt = g; tt < nk; tt += G) { int u0 = w.kbuf[tt] * S; v += p1[u0] * p2[-u0]; }
-      }
-      double tot = v;
-      for (int k = 1; k < G; ++k) tot += w_shfl_down(v, k * rem);
-      if (lane < rem) part[nfull + lane] = tot;
-    }
-    for (int a = lane; a < (G >= 2 ? nfull : h.n_split); a += WARP_N) {
+    for (int a = lane; a < h.n_split; a += WARP_N) {
       const double* p1 = r1 + ld_ro(h.sp_l + a);
       const double* p2 = r2 + ld_ro(h.sp_r + a);
       double v0 = 0., v1 = 0.;
@@ -1238,30 +1221,7 @@ template <int NCH, int MODE = 0> RDEV void lin_out_B(const LinCtx& c, const CTab
     // sibling 2(j, j') by right end: row i+d2, span d2-d -> offset ((i+d2)*W1 + d2-d)*S = base + d2*(W1+1)*S
     const int sib0 = (i * q.W1 - d) * S, sstep = (q.W1 + 1) * S;
     const unsigned rb = cidx(q, i, 0);
-    // last, partly filled round of the list: G lanes per entry, every G-th split point each (see lin_in_B)
-    const int nfull = (h.n_split / WARP_N) * WARP_N, rem = h.n_split - nfull;
-    const int G = rem > 0 ? WARP_N / rem : 1;
-    if (G >= 2) {
-      const int e = lane % rem, g = lane / rem;
-      double v[NCH];
-      for (int ch = 0; ch < NCH; ++ch) v[ch] = 0.;
-      if (g < G) {
-        int a = ld_ro(h.spL_ord + nfull + e);
-        const double* ps = t.a2 + sib0 + ld_ro(h.sp_r + a);
-        const double* pb = t.bBl + rb + ld_ro(h.sp_tgt + a);
-        for (int tt = g; tt < nk; tt += G) {
-          int da = w.kbuf[tt];
-          double sa = ps[da * sstep];
-          for (int ch = 0; ch < NCH; ++ch) v[ch] += pb[ch * t.bch + (unsigned)da * S] * sa;
-        }
-      }
-      for (int ch = 0; ch < NCH; ++ch) {
-        double tot = v[ch];
-        for (int k = 1; k < G; ++k) tot += w_shfl_down(v[ch], k * rem);
-        if (lane < rem) w.partA[ch * NM + nfull + lane] = tot;
-      }
-    }
-    for (int pz = lane; pz < (G >= 2 ? nfull : h.n_split); pz += WARP_N) {
+    for (int pz = lane; pz < h.n_split; pz += WARP_N) {
       int a = ld_ro(h.spL_ord + pz);
       int s = ld_ro(h.sp_tgt + a), sr = ld_ro(h.sp_r + a);
       double v[NCH], v2[NCH];
@@ -1310,29 +1270,7 @@ template <int NCH, int MODE = 0> RDEV void lin_out_B(const LinCtx& c, const CTab
     // sibling 1(i', i) by left end: row j-d2, span d2-d -> offset ((j-d2)*W1 + d2-d)*S = base - d2*(W1-1)*S
     const int sib0 = (j * q.W1 - d) * S, sstep = (q.W1 - 1) * S;
     const unsigned rb = cidx(q, j, 0);
-    const int nfull = (h.n_split / WARP_N) * WARP_N, rem = h.n_split - nfull;
-    const int G = rem > 0 ? WARP_N / rem : 1;
-    if (G >= 2) {
-      const int e = lane % rem, g = lane / rem;
-      double v[NCH];
-      for (int ch = 0; ch < NCH; ++ch) v[ch] = 0.;
-      if (g < G) {
-        int a = ld_ro(h.spR_ord + nfull + e);
-        const double* ps = t.a1 + sib0 + ld_ro(h.sp_l + a);
-        const double* pb = t.bBr + rb + ld_ro(h.sp_tgt + a);
-        for (int tt = g; tt < nk; tt += G) {
-          int da = w.kbuf[tt];
-          double sa = ps[-da * sstep];
-          for (int ch = 0; ch < NCH; ++ch) v[ch] += pb[ch * t.bch + (unsigned)da * S] * sa;
-        }
-      }
-      for (int ch = 0; ch < NCH; ++ch) {
-        double tot = v[ch];
-        for (int k = 1; k < G; ++k) tot += w_shfl_down(v[ch], k * rem);
-        if (lane < rem) w.partA[ch * NM + nfull + lane] = tot;
-      }
-    }
-    for (int pz = lane; pz < (G >= 2 ? nfull : h.n_split); pz += WARP_N) {
+    for (int pz = lane; pz < h.n_split; pz += WARP_N) {
       int a = ld_ro(h.spR_ord + pz);
       int s = ld_ro(h.sp_tgt + a), sl = ld_ro(h.sp_l + a);
       double v[NCH], v2[NCH];
