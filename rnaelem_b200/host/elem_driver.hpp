@@ -117,7 +117,6 @@ class RNAelemTrainer {
   RNAelemTrainer(unsigned mode, DeviceGroup& dev, OutputSet& out) : mode_(mode), dev_(dev), out_(out) {}
   void set_fq_name(const std::string& f) { qr_.open(f); }
   void set_conditions(int max_iter, double /*epsilon: L-BFGS-B only*/, double lambda_init, int kmer_shuf, int batch_size) {
-    check(!(mode_ & TR_NO_SHUFFLE), "--no-shuffle (L-BFGS-B) training is not available in this build");
     max_iter_ = max_iter; kmer_shuf_ = kmer_shuf; lambda_init_ = lambda_init;
     adam_.set_hp(0, 0, 0.1, 0.9, 0.999, 1.e-8);
     qr_.set_batch_size(batch_size);
@@ -125,7 +124,27 @@ class RNAelemTrainer {
   }
   int evaluations() const { return cnt_; }
 
+  // One full-batch objective evaluation of the model as it is: `fn:` on channel 1, `gr:` on channel 2, 17 digits
+  // (RNAelemTrainer::eval, motif_eval.hpp:22-53).  In the reference this sub-command never sets a batch size and
+  // evaluates zero reads; here it does what it was written for, at evaluation count 0, with
+  // shuffled negatives unless --no-shuffle.
+  void eval(MotifModel& model) {
+    motif_ = &model;
+    V x, gr;
+    model.pack(x);
+    dev_.set_model(model);
+    qr_.set_batch_size(-1);
+    cnt_ = 0;
+    double fn = 0.;
+    (*this)(x, fn, gr);
+    for (int id : {1, 2}) out_.at(id).precision(17);
+    out_.dat(1, "fn:", fn);
+    out_.dat(2, "gr:", gr);
+    for (int id : {1, 2}) out_.at(id).precision(6);
+  }
+
   void train(MotifModel& model) {
+    check(!(mode_ & TR_NO_SHUFFLE), "--no-shuffle training needs the L-BFGS-B optimizer, which is not available in this build");
     motif_ = &model;
     model.lambda[0] = model.lambda[1] = lambda_init_;
     V x;
@@ -177,9 +196,11 @@ class RNAelemTrainer {
     std::vector<char> flagged(nr, 0);
     std::vector<std::string> fail(nr);
     const int kshuf = kmer_shuf_, iter = cnt_;
-    parallel_for(nr, [&, kshuf, iter](int i) {
+    const bool shuffle = !(mode_ & TR_NO_SHUFFLE);   // without negatives a read is a unit of its own
+    parallel_for(nr, [&, kshuf, iter, shuffle](int i) {
       try {
         flagged[i] = quality_to_weights(rs[i]->qual, wv[i]) ? 1 : 0;
+        if (!shuffle) return;
         std::string neg = shuffled_negative(codes_to_text(rs[i]->seq), kshuf, iter);
         negv[i].resize(neg.size());
         for (size_t k = 0; k < neg.size(); ++k) negv[i][k] = base_code(neg[k]);
@@ -191,7 +212,7 @@ class RNAelemTrainer {
     for (int i = 0; i < nr; ++i) {
       int me = b.n();
       b.add(rs[i]->seq, wv[i], flagged[i] ? RELEM_POS_WITH : lr ? RELEM_LR_WITHOUT : RELEM_POS_WITHOUT, -1, rs[i]->id);
-      b.add(negv[i], V(negv[i].size(), 0.), lr ? RELEM_LR_NEG : RELEM_NEG, me, rs[i]->id);   // qualities all 0 -> weight 0
+      if (shuffle) b.add(negv[i], V(negv[i].size(), 0.), lr ? RELEM_LR_NEG : RELEM_NEG, me, rs[i]->id);   // qualities all 0 -> weight 0
     }
     const double ms_pack = lapse();
     dev_.push_params(*motif_);
@@ -204,9 +225,10 @@ class RNAelemTrainer {
     std::vector<V> part(nw);
     dev_.each([&](int k) {
       // shards are cut between (positive, negative) pairs so that a gate never crosses ranks
+      const int unit = shuffle ? 2 : 1;
       long p0, p1;
-      shard_range(b.n() / 2, nw, k, p0, p1);
-      int s0 = int(2 * p0), ns = int(2 * (p1 - p0));
+      shard_range(b.n() / unit, nw, k, p0, p1);
+      int s0 = int(unit * p0), ns = int(unit * (p1 - p0));
       std::vector<int64_t> off(b.off.begin() + s0, b.off.begin() + s0 + ns + 1);
       std::vector<int32_t> gate(b.gate.begin() + s0, b.gate.begin() + s0 + ns);
       for (auto& o : off) o -= b.off[s0];

@@ -4,8 +4,9 @@
 // (RNAelem/main.cpp:19-163, application.hpp:76-410), so `script/elem` can call this binary in its place.  Host work
 // (reading, negative generation, Adam, writers) is elem_host.hpp / elem_driver.hpp; every DP pass is a librelem call.
 // One addition: --gpus N (or RELEM_GPUS) shards each minibatch / scan over N GPUs of the box.  `-t/--thread` is
-// accepted and ignored (the batch runs on the GPU).  Sub-commands that only exist for the reference's Grid Engine
-// fan-out or debugging (array-eval, eval, develop, logo) are refused.
+// accepted and ignored (the batch runs on the GPU).  `eval` prints the full-batch objective and gradient of a model
+// with 17 digits.  Sub-commands that only exist for the reference's Grid Engine fan-out or drawing (array-eval, develop,
+// logo) are refused.
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
@@ -104,20 +105,21 @@ void model_from_options(const Options& o, MotifModel& m) {
 
 int run(int argc, const char* const* argv) {
   Options o = parse_command_line(argc, argv);
-  enum { NORMAL, TRAIN, SCAN, GENNEG } mode = NORMAL;
+  enum { NORMAL, TRAIN, SCAN, GENNEG, EVAL } mode = NORMAL;
   if (!o.args.empty()) {
     const std::string& c = o.args[0];
     if (c == "train") mode = TRAIN;
     else if (c == "scan") mode = SCAN;
     else if (c == "gen-neg") mode = GENNEG;
-    else if (c == "array-eval" || c == "eval" || c == "develop" || c == "logo")
+    else if (c == "eval") mode = EVAL;
+    else if (c == "array-eval" || c == "develop" || c == "logo")
       die("sub-command not available in the B200 build:", c);
     else die("unknown sub-command:", o.args);
   }
   OutputSet out(4);
   out.bind(1, o.str("out1")); out.bind(2, o.str("out2")); out.bind(3, o.str("out3"));
   check(o.str("seq_fname") != "~NONE~", "require input filename (sequence)");
-  if (mode == SCAN) check(o.str("model_fname") != "~NONE~", "require input filename (motif model)");
+  if (mode == SCAN || mode == EVAL) check(o.str("model_fname") != "~NONE~", "require input filename (motif model)");
   check(o.num("array") <= 1, "Grid Engine array jobs are replaced by --gpus in the B200 build");
   check(o.str("param_set").empty(), "--param-set (masked training) is not available in the B200 build");
 
@@ -146,6 +148,16 @@ int run(int argc, const char* const* argv) {
   if (o.str("model_fname") != "~NONE~") read_model(o.str("model_fname"), model);
   else if (mode != SCAN) model_from_options(o, model);
 
+  if (mode == EVAL) {   // main.cpp:31-46
+    unsigned tr = TR_NORMAL;
+    if (o.flag("no_shuffle")) tr |= TR_NO_SHUFFLE;
+    if (o.flag("lik_ratio")) tr |= TR_LIK_RATIO;
+    RNAelemTrainer trainer(tr, dev, out);
+    trainer.set_fq_name(o.str("seq_fname"));
+    trainer.set_conditions(1, o.real("eps"), 0., o.num("kmer_shuf"), -1);
+    trainer.eval(model);
+    return 0;
+  }
   if (mode == NORMAL || mode == TRAIN) {
     unsigned tr = TR_NORMAL;
     if (o.flag("no_shuffle")) tr |= TR_NO_SHUFFLE;

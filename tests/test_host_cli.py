@@ -93,3 +93,40 @@ def test_model_written_here_is_read_by_the_reference(emu_cli, tmp_path):
         outs[name] = (open(raw).read(), p.stderr)
     clilib.compare_text(outs["ref"][0], outs["ours"][0], "scan.raw with a model written here")
     clilib.compare_text(outs["ref"][1], outs["ours"][1], "scan stderr")
+
+
+def _eval_case(binary, name, tmp_path):
+    """`RNAelem eval` through the whole host stack (FASTQ reader, weights, negatives, packing, chain rule, lambda slots)
+    against the fn / gr the unmodified reference computed for the same model and reads (tests/golden/case_*.json)."""
+    import re
+    import caselib
+    case = caselib.load_case(name)
+    model = tmp_path / "m.model"
+    fq = tmp_path / "in.fq"
+    model.write_text(case["model_text"])
+    with open(fq, "w") as f:
+        for r in case["records"]:
+            f.write("%s\n%s\n+\n%s\n" % (r["id"], r["seq"], "".join(chr(33 + q) for q in r["qual"])))
+    cmd = [binary, "eval", "-f", str(fq), "-q", str(model), "--out1", str(tmp_path / "fn.txt"), "--out2", str(tmp_path / "gr.txt")]
+    if not case["shuffle"]:
+        cmd.append("--no-shuffle")
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    fn = float((tmp_path / "fn.txt").read_text().split(": ")[1])
+    gr = [float(x) for x in re.findall(r"-?(?:inf|nan|\d+\.?\d*(?:[eE][-+]?\d+)?)", (tmp_path / "gr.txt").read_text().split(": ")[1])]
+    est = case["estep"]
+    assert caselib.close(fn, est["fn"]), (fn, est["fn"])
+    import numpy as np
+    summ = max(1.0, max(float(np.max(np.abs(e["ENo"]))) for e in est["per_seq"] if not e["skipped"]))
+    caselib.assert_close_vec(gr, est["gr"], name + " eval gr", scale=summ)
+
+
+@pytest.mark.parametrize("name", ["m0", "m1", "m2", "m3", "trna", "ragged"])
+def test_eval_emulated(name, emu_cli, tmp_path):
+    _eval_case(emu_cli, name, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["m0", "m1", "m2", "m3", "trna", "ragged", "synth200", "a2007_w150"])
+def test_eval_gpu(name, product_cli, tmp_path):
+    _eval_case(product_cli, name, tmp_path)
