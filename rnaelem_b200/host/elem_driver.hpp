@@ -207,43 +207,41 @@ class RNAelemTrainer {
       } catch (std::exception& e) { fail[i] = e.what(); }
     });
     for (auto& f : fail) if (!f.empty()) throw std::runtime_error(f);
-    PackedBatch b;
     const bool lr = (mode_ & TR_LIK_RATIO) != 0;   // likelihood-ratio objective: motif_trainer.hpp:156-202
-    for (int i = 0; i < nr; ++i) {
-      int me = b.n();
-      b.add(rs[i]->seq, wv[i], flagged[i] ? RELEM_POS_WITH : lr ? RELEM_LR_WITHOUT : RELEM_POS_WITHOUT, -1, rs[i]->id);
-      if (shuffle) b.add(negv[i], V(negv[i].size(), 0.), lr ? RELEM_LR_NEG : RELEM_NEG, me, rs[i]->id);   // qualities all 0 -> weight 0
-    }
     const double ms_pack = lapse();
     dev_.push_params(*motif_);
     const double ms_push = lapse();
 
+    // Every rank packs and evaluates its contiguous block of reads (a read travels with the negative shuffled from
+    // it, so a gate never crosses ranks), then the partial sums meet in one all-reduce.
     const int nth = motif_->n_theta(), nw = dev_.size();
     V en(nth, 0.);
     double eh[2] = {0., 0.};
-    std::vector<uint8_t> skipped(b.n(), 0);
     std::vector<V> part(nw);
+    std::vector<std::vector<std::string>> skipped_ids(nw);
     dev_.each([&](int k) {
-      // shards are cut between (positive, negative) pairs so that a gate never crosses ranks
-      const int unit = shuffle ? 2 : 1;
       long p0, p1;
-      shard_range(b.n() / unit, nw, k, p0, p1);
-      int s0 = int(unit * p0), ns = int(unit * (p1 - p0));
-      std::vector<int64_t> off(b.off.begin() + s0, b.off.begin() + s0 + ns + 1);
-      std::vector<int32_t> gate(b.gate.begin() + s0, b.gate.begin() + s0 + ns);
-      for (auto& o : off) o -= b.off[s0];
-      for (auto& g : gate) if (g >= 0) g -= s0;
+      shard_range(nr, nw, k, p0, p1);
+      PackedBatch b;
+      for (long i = p0; i < p1; ++i) {
+        int me = b.n();
+        b.add(rs[i]->seq, wv[i], flagged[i] ? RELEM_POS_WITH : lr ? RELEM_LR_WITHOUT : RELEM_POS_WITHOUT, -1, rs[i]->id);
+        if (shuffle) b.add(negv[i], V(negv[i].size(), 0.), lr ? RELEM_LR_NEG : RELEM_NEG, me, rs[i]->id);   // qualities all 0 -> weight 0
+      }
+      const int ns = b.n();
+      std::vector<uint8_t> skipped(ns, 0);
       V& v = part[k];
       v.assign(nth + 5, 0.);   // fn, sum_eff, n_skipped, EN_diff[nth], EH_diff[2]
       relem_estep_out o;
       std::memset(&o, 0, sizeof o);
       o.EN_diff = v.data() + 3;
-      o.skipped = skipped.data() + s0;
+      o.skipped = skipped.data();
       if (ns > 0)
-        dev_.ok(k, relem_estep(dev_.ctx(k), ns, b.seq.data() + b.off[s0], off.data(), b.ws.data() + b.off[s0],
-                               b.kind.data() + s0, gate.data(), &o), "relem_estep");
+        dev_.ok(k, relem_estep(dev_.ctx(k), ns, b.seq.data(), b.off.data(), b.ws.data(), b.kind.data(), b.gate.data(), &o),
+                "relem_estep");
       v[0] = o.fn; v[1] = o.sum_eff; v[2] = double(o.n_skipped);
       v[3 + nth] = o.EH_diff[0]; v[4 + nth] = o.EH_diff[1];
+      for (int n = 0; n < ns; ++n) if (skipped[n] == 1) skipped_ids[k].push_back(b.id[n]);
       if (nw > 1) dev_.ok(k, relem_allreduce_sum(dev_.ctx(k), v.data(), int(v.size())), "relem_allreduce_sum");
     });
     const double ms_estep = lapse();
@@ -259,7 +257,7 @@ class RNAelemTrainer {
     for (int k = 0; k < nth; ++k) en[k] = tot[3 + k];
     eh[0] = tot[3 + nth]; eh[1] = tot[4 + nth];
     if (cnt_ == 0)
-      for (int k = 0; k < b.n(); ++k) if (skipped[k] == 1) cry("skipped:", b.id[k]);
+      for (const auto& ids : skipped_ids) for (const std::string& id : ids) cry("skipped:", id);
 
     // RNAelemTrainDP's update block (motif_trainer.hpp:248-271)
     int k = 0;
