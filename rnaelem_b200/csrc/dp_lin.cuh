@@ -32,6 +32,11 @@
 #include "dp_prim.cuh"
 #include "lin_model.hpp"
 
+// split points a lane of the split gathers keeps in flight (2 or 4)
+#ifndef LIN_SPLIT_UNROLL
+#define LIN_SPLIT_UNROLL 2
+#endif
+
 namespace relem {
 namespace lin {
 using namespace relem::dp;
@@ -810,6 +815,16 @@ RDEV void lin_in_B(const LinCtx& c, const CTabs& t, int i, int d, bool gP, bool 
       const double* p2 = r2 + ld_ro(h.sp_r + a);
       double v0 = 0., v1 = 0.;
       int tt = 0;
+#if LIN_SPLIT_UNROLL >= 4
+      double v2 = 0., v3 = 0.;
+      for (; tt + 3 < nk; tt += 4) {   // four split points in flight
+        int u0 = w.kbuf[tt] * S, u1 = w.kbuf[tt + 1] * S, u2 = w.kbuf[tt + 2] * S, u3 = w.kbuf[tt + 3] * S;
+        double a0 = p1[u0], a1 = p1[u1], a2 = p1[u2], a3 = p1[u3];
+        double b0 = p2[-u0], b1 = p2[-u1], b2 = p2[-u2], b3 = p2[-u3];
+        v0 += a0 * b0; v1 += a1 * b1; v2 += a2 * b2; v3 += a3 * b3;
+      }
+      v0 += v2; v1 += v3;
+#endif
       for (; tt + 1 < nk; tt += 2) {
         int u0 = w.kbuf[tt] * S, u1 = w.kbuf[tt + 1] * S;
         v0 += p1[u0] * p2[-u0];
@@ -1229,6 +1244,18 @@ template <int NCH, int MODE = 0> RDEV void lin_out_B(const LinCtx& c, const CTab
       const double* ps = t.a2 + sib0 + sr;
       const double* pb = t.bBl + rb + s;
       int tt = 0;
+#if LIN_SPLIT_UNROLL >= 4
+      if (NCH == 1) {
+        double v3 = 0., v4 = 0.;
+        for (; tt + 3 < nk; tt += 4) {   // four split points in flight
+          int da = w.kbuf[tt], db = w.kbuf[tt + 1], dc = w.kbuf[tt + 2], de = w.kbuf[tt + 3];
+          double sa = ps[da * sstep], sb = ps[db * sstep], sc = ps[dc * sstep], se = ps[de * sstep];
+          double ba = pb[(unsigned)da * S], bb = pb[(unsigned)db * S], bc = pb[(unsigned)dc * S], be = pb[(unsigned)de * S];
+          v[0] += ba * sa; v2[0] += bb * sb; v3 += bc * sc; v4 += be * se;
+        }
+        v[0] += v3; v2[0] += v4;
+      }
+#endif
       for (; tt + 1 < nk; tt += 2) {   // two split points in flight
         int da = w.kbuf[tt], db = w.kbuf[tt + 1];
         double sa = ps[da * sstep], sb = ps[db * sstep];
@@ -1278,6 +1305,18 @@ template <int NCH, int MODE = 0> RDEV void lin_out_B(const LinCtx& c, const CTab
       const double* ps = t.a1 + sib0 + sl;
       const double* pb = t.bBr + rb + s;
       int tt = 0;
+#if LIN_SPLIT_UNROLL >= 4
+      if (NCH == 1) {
+        double v3 = 0., v4 = 0.;
+        for (; tt + 3 < nk; tt += 4) {
+          int da = w.kbuf[tt], db = w.kbuf[tt + 1], dc = w.kbuf[tt + 2], de = w.kbuf[tt + 3];
+          double sa = ps[-da * sstep], sb = ps[-db * sstep], sc = ps[-dc * sstep], se = ps[-de * sstep];
+          double ba = pb[(unsigned)da * S], bb = pb[(unsigned)db * S], bc = pb[(unsigned)dc * S], be = pb[(unsigned)de * S];
+          v[0] += ba * sa; v2[0] += bb * sb; v3 += bc * sc; v4 += be * se;
+        }
+        v[0] += v3; v2[0] += v4;
+      }
+#endif
       for (; tt + 1 < nk; tt += 2) {
         int da = w.kbuf[tt], db = w.kbuf[tt + 1];
         double sa = ps[-da * sstep], sb = ps[-db * sstep];
