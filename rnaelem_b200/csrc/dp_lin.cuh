@@ -34,7 +34,7 @@
 
 // split points a lane of the split gathers keeps in flight (2 or 4)
 #ifndef LIN_SPLIT_UNROLL
-#define LIN_SPLIT_UNROLL 2
+#define LIN_SPLIT_UNROLL 4   // measured: 9 442 -> 9 532 sequence-evaluations/s at 64 registers, no spills
 #endif
 
 namespace relem {
