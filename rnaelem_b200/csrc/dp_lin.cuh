@@ -32,6 +32,14 @@
 #include "dp_prim.cuh"
 #include "lin_model.hpp"
 
+// unroll factor of the candidate loops of the interior-loop / exterior gathers (experiment switch; 1 = compiler default)
+#if defined(LIN_PP_UNROLL) && LIN_PP_UNROLL == 2 && !defined(RELEM_HOST_EMU)
+#define LIN_PP_PRAGMA _Pragma("unroll 2")
+#elif defined(LIN_PP_UNROLL) && LIN_PP_UNROLL == 4 && !defined(RELEM_HOST_EMU)
+#define LIN_PP_PRAGMA _Pragma("unroll 4")
+#else
+#define LIN_PP_PRAGMA
+#endif
 // split points a lane of the split gathers keeps in flight (2 or 4)
 #ifndef LIN_SPLIT_UNROLL
 #define LIN_SPLIT_UNROLL 4   // measured: 9 442 -> 9 532 sequence-evaluations/s at 64 registers, no spills
@@ -909,6 +917,7 @@ RDEV void lin_in_E(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpL
         int s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a), s3 = ld_ro(h.q_s3 + a);
         const double* bf = ld_ro(h.slot + ld_ro(h.q_tgt + a)) ? w.bf1 : w.bf0;
         double v = part[a];
+        LIN_PP_PRAGMA
         for (int pp = 0; pp < n; ++pp) {
           int k = w.bi[pp], l = w.bj[pp];
           double a0 = t.aP[cidx(q, l, l - k) + s1];
@@ -985,6 +994,7 @@ RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
         int sl = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
         const double* bf = ld_ro(h.slot + ld_ro(h.sp_tgt + a)) ? w.bf1 : w.bf0;
         double v = part[a];
+        LIN_PP_PRAGMA
         for (int pp = 0; pp < n; ++pp) {
           int i = w.bi[pp];
           v += t.aO[(unsigned)i * S + sl] * t.aP[cidx(q, j, j - i) + sr] * bf[pp];
@@ -1062,6 +1072,7 @@ template <int NCH, int MODE = 0> RDEV void lin_outside_ext(const LinCtx& c, cons
         const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
         double v[NCH];
         for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
+        LIN_PP_PRAGMA
         for (int pp = 0; pp < n; ++pp) {
           int j = w.bi[pp];
           double term = t.aP[cidx(q, j, j - i) + sr] * bf[pp];
@@ -1491,6 +1502,7 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
         const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
         double v[NCH], vt[NCH];
         for (int ch = 0; ch < NCH; ++ch) { v[ch] = w.partA[ch * NM + pz]; vt[ch] = w.partT[ch * NM + pz]; }
+        LIN_PP_PRAGMA
         for (int pp = 0; pp < n; ++pp) {
           int i2 = w.bi[pp], j2 = w.bj[pp];
           double term = t.aLl[cidx(q, i2, i - i2) + s2] * t.aLr[cidx(q, j2, j2 - j) + s3] * bf[pp];
@@ -1613,7 +1625,8 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
           const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
           double v[NCH];
           for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
-          for (int pp = 0; pp < n; ++pp) {
+          LIN_PP_PRAGMA
+        for (int pp = 0; pp < n; ++pp) {
             int l = w.bi[pp], j2 = w.bj[pp];
             double term = t.aP[cidx(q, l, l - j) + s1] * t.aLr[cidx(q, j2, j2 - l) + s3] * bf[pp];
             for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEl[ch * t.bch + eb + (unsigned)(j2 - i) * S + s] * term;
@@ -1643,7 +1656,8 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
           const double* bf = ld_ro(h.slot + s) ? w.bf1 : w.bf0;
           double v[NCH];
           for (int ch = 0; ch < NCH; ++ch) v[ch] = w.partA[ch * NM + pz];
-          for (int pp = 0; pp < n; ++pp) {
+          LIN_PP_PRAGMA
+        for (int pp = 0; pp < n; ++pp) {
             int k = w.bi[pp], i2 = w.bj[pp];
             double term = t.aP[cidx(q, i, i - k) + s1] * t.aLl[cidx(q, i2, k - i2) + s2] * bf[pp];
             for (int ch = 0; ch < NCH; ++ch) v[ch] += t.bEr[ch * t.bch + eb + (unsigned)(j - i2) * S + s] * term;
