@@ -148,6 +148,12 @@ void relem_assigned_range(int64_t total, int n, int k, int64_t* from, int64_t* t
  * of kernel launches it made; names[i] are static strings.  returns the number of entries (<= cap). */
 int relem_last_timing(const relem_ctx*, const char** names, float* ms, int* launches, int cap);
 
+/* fp64 pipe peaks of this GPU by micro-benchmark (a few ms; SURVEY.md 8d asks for them because MEASURED_PEAKS.json
+ * only has HBM and bf16): dfma_per_s = double-precision fused multiply-adds per second with every SM busy
+ * (8 independent chains per thread), exp_per_s = libm-accurate exp() evaluations per second.  The reference has no
+ * counterpart: its inner loops spend their time in logsumexp (util.hpp:195-202), two libm calls per term. */
+int relem_fp64_peak(relem_ctx*, double* dfma_per_s, double* exp_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,7 @@ SYMBOLS = ["relem_version", "relem_create", "relem_destroy", "relem_last_error",
            "relem_set_pattern", "relem_model_dims", "relem_theta_rows", "relem_hmm_get", "relem_energy_get",
            "relem_set_params", "relem_batch_create", "relem_batch_destroy", "relem_batch_cells", "relem_estep_run",
            "relem_estep", "relem_bpp", "relem_scan_run", "relem_scan", "relem_comm_unique_id", "relem_comm_init",
-           "relem_allreduce_sum", "relem_assigned_range", "relem_last_timing"]
+           "relem_allreduce_sum", "relem_assigned_range", "relem_last_timing", "relem_fp64_peak"]
 
 
 def load_library(path=None):
@@ -81,6 +81,7 @@ def load_library(path=None):
     lib.relem_assigned_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.relem_assigned_range.restype = None
     lib.relem_last_timing.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), ip, C.c_int]
+    lib.relem_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _LIBS[path] = lib
     return lib
 
@@ -231,6 +232,10 @@ class Context(object):
 
     def estep(self, seq_cat, off, ws_cat, kind=None, gate=None, detail=False):
         """host buffers in, host results out (the reference-facing call)."""
+        # same coercion as batch(): a wrong dtype or a strided view would be reinterpreted by the C side
+        seq_cat = np.ascontiguousarray(seq_cat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        ws_cat = np.ascontiguousarray(ws_cat, dtype=np.float64)
         nseq = len(off) - 1
         r, o = self._estep_out(nseq, detail)
         kind = None if kind is None else np.ascontiguousarray(kind, dtype=np.uint8)
@@ -257,8 +262,8 @@ class Context(object):
     def _max_span(self):
         return getattr(self, "_ms", 1 << 30)
 
-    def scan_run(self, batch):
-        nseq, tl, NT = batch.nseq, int(batch.off[-1]), self.n_theta
+    def _scan_out(self, nseq, tl):
+        NT = self.n_theta
         r = ScanResult()
         r.PysL = np.zeros(tl); r.PyeL = np.zeros(tl + nseq); r.PyiL = np.zeros(tl)
         r.psihat = np.zeros(tl, dtype=np.int32); r.rss_buf = C.create_string_buffer(tl + 1)
@@ -270,15 +275,38 @@ class Context(object):
         o.rss = C.cast(r.rss_buf, C.c_char_p)
         o.Ys = r.Ys.ctypes.data_as(C.POINTER(C.c_int32)); o.Ye = r.Ye.ctypes.data_as(C.POINTER(C.c_int32))
         o.exist_prob, o.EN, o.ZL = _dptr(r.exist_prob), _dptr(r.EN), _dptr(r.ZL)
+        return r, o
+
+    def scan_run(self, batch):
+        nseq, tl = batch.nseq, int(batch.off[-1])
+        r, o = self._scan_out(nseq, tl)
         self._check(self.lib.relem_scan_run(self.h, batch.handle, C.byref(o)), "relem_scan_run")
         r.rss = r.rss_buf.raw[:tl].decode("ascii")
         r.off = batch.off
         return r
 
+    def scan(self, seq_cat, off, ws_cat, decode_rss=True):
+        """host buffers in, host results out (the reference-facing call: RNAelemScanner::scan, motif_scanner.hpp:938-949)."""
+        seq_cat = np.ascontiguousarray(seq_cat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        ws_cat = np.ascontiguousarray(ws_cat, dtype=np.float64)
+        nseq, tl = len(off) - 1, int(off[-1])
+        r, o = self._scan_out(nseq, tl)
+        self._check(self.lib.relem_scan(self.h, nseq, _ptr(seq_cat), _ptr(off), _ptr(ws_cat), C.byref(o)), "relem_scan")
+        r.rss = r.rss_buf.raw[:tl].decode("ascii") if decode_rss else None
+        r.off = off
+        return r
+
     def timing(self):
-        names = (C.c_char_p * 16)(); ms = (C.c_float * 16)(); ln = (C.c_int * 16)()
-        n = self.lib.relem_last_timing(self.h, names, ms, ln, 16)
+        names = (C.c_char_p * 48)(); ms = (C.c_float * 48)(); ln = (C.c_int * 48)()
+        n = self.lib.relem_last_timing(self.h, names, ms, ln, 48)
         return [(names[k].decode(), float(ms[k]), int(ln[k])) for k in range(n)]
+
+    def fp64_peak(self):
+        """-> (DFMA per second, exp() per second) measured on this GPU"""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.relem_fp64_peak(self.h, C.byref(a), C.byref(b)), "relem_fp64_peak")
+        return a.value, b.value
 
     # ---- collective
     def comm_init(self, uid_bytes, rank, nranks):

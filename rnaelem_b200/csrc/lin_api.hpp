@@ -62,6 +62,12 @@ struct LinScanLaunch {
 int lin_scan_launch(LinState*, const LinScanLaunch&, lin_chunk_fn after_chunk, void* user, float* kernel_ms, int* launches,
                     std::string& err);
 
+// per-phase device time of the last lin_estep_launch that ran under RELEM_PHASE_TIMING=1 (static names)
+int lin_phase_timing(const LinState*, const char** names, float* ms, int* launches, int cap);
+
+// fp64 micro-benchmark (relem_fp64_peak): fused multiply-adds / exp() per second on the given stream's device
+int lin_fp64_peak(void* stream, int sm_count, double* dfma_per_s, double* exp_per_s, std::string& err);
+
 }  // namespace lin
 }  // namespace relem
 #endif

@@ -673,6 +673,13 @@ int relem_estep_run(relem_ctx* c, relem_batch* b, relem_estep_out* out) {
     } else {
       if (lrc) return fail(c, lrc == 3 ? RELEM_ENOMEM : RELEM_ECUDA, "linear-space E-step: " + lerr);
       c->timing.push_back(TimingEntry{"relem_estep_lin_kernel", ms, nl});
+      {
+        // RELEM_PHASE_TIMING=1: per-phase-class device time, reported with zero launches so that sums over entries
+        // with launches > 0 stay the whole-call figures
+        const char* pn[16]; float pms[16]; int pl[16];
+        int np = lin::lin_phase_timing(c->lin, pn, pms, pl, 16);
+        for (int k = 0; k < np; ++k) c->timing.push_back(TimingEntry{pn[k], pms[k], -pl[k]});
+      }
       std::vector<unsigned char> flags(nseq);
       if (!Dev::d2h(flags.data(), c->d_flag.p, nseq)) return fail(c, RELEM_ECUDA, "flag copy failed");
       std::vector<int> redo;
@@ -988,6 +995,19 @@ int relem_last_timing(const relem_ctx* c, const char** names, float* ms, int* la
     if (launches) launches[k] = c->timing[k].launches;
   }
   return n;
+}
+
+int relem_fp64_peak(relem_ctx* c, double* dfma_per_s, double* exp_per_s) {
+  if (!c) return RELEM_EINVAL;
+  if (!bind_device(c)) return fail(c, RELEM_ECUDA, "cudaSetDevice failed");
+  std::string err;
+#ifndef RELEM_HOST_EMU
+  int rc = lin::lin_fp64_peak((void*)c->stream, c->sm_count, dfma_per_s, exp_per_s, err);
+#else
+  int rc = lin::lin_fp64_peak(nullptr, 1, dfma_per_s, exp_per_s, err);
+#endif
+  if (rc) return fail(c, rc == 3 ? RELEM_ENOMEM : rc == 1 ? RELEM_EINVAL : RELEM_ECUDA, "fp64 micro-benchmark: " + err);
+  return RELEM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------- NCCL

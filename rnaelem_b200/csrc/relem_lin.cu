@@ -37,6 +37,7 @@ using namespace relem::dp;
 
 #define LIN_THREADS 128
 #define LIN_WARPS (LIN_THREADS / 32)
+#define LIN_NPHASE_SLOTS 16
 
 struct LinLayout {
   unsigned long long stride;  // doubles per slot
@@ -667,7 +668,10 @@ struct LinState {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t lane[4] = {nullptr, nullptr, nullptr, nullptr};  // two chunks in flight: one fills the SMs while the other's kernel drains
   cudaEvent_t lane_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_pool;   // RELEM_PHASE_TIMING: one event pair per phase launch
 #endif
+  float phase_ms[LIN_NPHASE_SLOTS] = {0};   // device time per phase class of the last instrumented launch
+  int phase_launches[LIN_NPHASE_SLOTS] = {0};
 };
 
 LinState* lin_state_create() { return new LinState(); }
@@ -684,6 +688,7 @@ void lin_state_destroy(LinState* s) {
     if (s->lane[k]) cudaStreamDestroy(s->lane[k]);
     if (s->lane_done[k]) cudaEventDestroy(s->lane_done[k]);
   }
+  for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
 #endif
   delete s;
 }
@@ -701,8 +706,22 @@ struct Runner {
   int tile_f = 64, tile_q = 256;   // flank kernels of outside L, interior-loop kernel of outside P
 #ifdef RELEM_HOST_EMU
   std::vector<unsigned char> smem;
+  void mark(int) {}
 #else
   cudaStream_t stream;
+  // RELEM_PHASE_TIMING=1 (one lane): an event before and after every phase launch, summed per phase class afterwards
+  LinState* st = nullptr;
+  bool timing = false;
+  std::vector<int> marks;   // phase id of event pair k (events 2k, 2k+1 of the pool)
+  void mark(int ph) {
+    if (!timing) return;
+    const size_t k = marks.size() * 2 + (open_ ? 1 : 0);
+    while (st->ev_pool.size() <= k) { cudaEvent_t e; cudaEventCreate(&e); st->ev_pool.push_back(e); }
+    cudaEventRecord(st->ev_pool[k], stream);
+    if (open_) marks.push_back(ph);
+    open_ = !open_;
+  }
+  bool open_ = false;
 #endif
 };
 }  // namespace
@@ -736,7 +755,9 @@ template <int PH, int NCH> static void launch_phase(Runner& r, int d, int tile, 
   if (tile > ncell_max) tile = ncell_max;
   tile = fit_tile(r, tile, ncell_max);
   r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile; r.a.win = 0;
+  r.mark(PH);
   LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, NCH>), r.a.count * r.a.ntile, LIN_THREADS, smem);
+  r.mark(PH);
 }
 
 // inside phase of the scanner's second pass: at most d + 2 cells per sequence contain Ys (see the kernel)
@@ -747,7 +768,9 @@ template <int PH> static void launch_phase_win(Runner& r, int d, int tile, int s
   if (tile > ncell_max) tile = ncell_max;
   tile = fit_tile(r, tile, ncell_max);
   r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile; r.a.win = 1;
+  r.mark(PH);
   LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, 1>), r.a.count * r.a.ntile, LIN_THREADS, smem);
+  r.mark(PH);
 }
 
 template <int PH, int MODE> static void launch_phase3(Runner& r, int d, int tile, int smem) {
@@ -756,7 +779,9 @@ template <int PH, int MODE> static void launch_phase3(Runner& r, int d, int tile
   if (tile > ncell_max) tile = ncell_max;
   tile = fit_tile(r, tile, ncell_max);
   r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile; r.a.win = 0;
+  r.mark(PH);
   LIN_LAUNCH(r, (relem_lin_phase_kernel<PH, 1, MODE>), r.a.count * r.a.ntile, LIN_THREADS, smem);
+  r.mark(PH);
 }
 
 template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
@@ -882,6 +907,7 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   r.smem_ext_in = lay.sm_warp + lay.warp_bytes_in;
   r.smem_ext_out = lay.sm_warp + lay.warp_bytes_out;
   r.cmax = std::min(30, std::min((int)in.en.max_iloop, lay.Wmax - 7));
+  if (in.sm_count > 0) r.resident_ctas = in.sm_count * 7;
   const int NT = in.p.n_theta;
   if (const char* e = std::getenv("RELEM_FILL")) r.fill = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("RELEM_TILE_K0")) r.tile_k0 = std::max(4, std::atoi(e));
@@ -935,7 +961,11 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   // four lanes are no better.  Not when memory forces chunks so small that halving them would starve a launch.
   int nlanes = ((nseq >= 64 && by_mem >= nseq) || (nseq >= 4096 && by_mem >= 2048)) ? 2 : 1;
   if (const char* e = std::getenv("RELEM_LANES")) nlanes = std::max(1, std::min(4, std::atoi(e)));
-  long long nslots = std::min<long long>((nseq + nlanes - 1) / nlanes, by_mem / nlanes);
+  r.st = st;
+  if (const char* e = std::getenv("RELEM_PHASE_TIMING")) r.timing = std::atoi(e) != 0;
+  if (r.timing) nlanes = 1;   // per-launch events only mean something when nothing else shares the GPU
+  if (nlanes > by_mem) nlanes = (int)by_mem;   // every lane needs at least one slot
+  long long nslots = std::max<long long>(1, std::min<long long>((nseq + nlanes - 1) / nlanes, by_mem / nlanes));
   // keep an existing scratch buffer when it is close to what we would ask for (free memory fluctuates a little
   // from call to call; re-allocating ~100 GB costs more than a slightly smaller chunk)
   const long long have = (long long)(st->scratch_bytes / ((size_t)nlanes * per));
@@ -1000,8 +1030,33 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   cudaEventElapsedTime(&ms, e0, e1);
   if (kernel_ms) *kernel_ms = ms;
   if (launches) *launches = r.launches;
+  for (int k = 0; k < LIN_NPHASE_SLOTS; ++k) { st->phase_ms[k] = 0.f; st->phase_launches[k] = 0; }
+  for (size_t k = 0; k < r.marks.size(); ++k) {
+    float pm = 0.f;
+    cudaEventElapsedTime(&pm, st->ev_pool[2 * k], st->ev_pool[2 * k + 1]);
+    st->phase_ms[r.marks[k]] += pm;
+    st->phase_launches[r.marks[k]] += 1;
+  }
   return 0;
 #endif
+}
+
+int lin_phase_timing(const LinState* st, const char** names, float* ms, int* launches, int cap) {
+  static const char* kName[LIN_NPHASE_SLOTS] = {
+      "relem_lin_phase_kernel<0> K0 inside", "relem_lin_phase_kernel<1> K0 outside", "relem_lin_phase_kernel<2> inside L",
+      "relem_lin_phase_kernel<3> inside P", "relem_lin_phase_kernel<4> inside B,2,1,M", "relem_lin_phase_kernel<5> inside E",
+      "relem_lin_phase_kernel<6> outside E,M", "relem_lin_phase_kernel<7> outside 1,B,2",
+      "relem_lin_phase_kernel<8> outside P (2<-P, stack, exterior)", "relem_lin_phase_kernel<9> outside L (hairpin, parent)",
+      "relem_lin_phase_kernel<10> outside L left flanks", "relem_lin_phase_kernel<11> outside L right flanks",
+      "relem_lin_phase_kernel<12> outside P enclosing interior loops", "", "", ""};
+  int n = 0;
+  if (!st) return 0;
+  for (int k = 0; k < LIN_NPHASE_SLOTS && n < cap; ++k) {
+    if (!st->phase_launches[k]) continue;
+    names[n] = kName[k]; ms[n] = st->phase_ms[k]; launches[n] = st->phase_launches[k];
+    ++n;
+  }
+  return n;
 }
 
 int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_chunk, void* user, float* kernel_ms,
@@ -1083,8 +1138,8 @@ int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_ch
   if (e == cudaSuccess) e = cudaStreamSynchronize(r.stream);
   if (e != cudaSuccess) { err = std::string("constant upload: ") + cudaGetErrorString(e); return 2; }
   a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  if (!st->ev0) { cudaEventCreate(&st->ev0); cudaEventCreate(&st->ev1); }
+  cudaEvent_t e0 = st->ev0, e1 = st->ev1;   // owned by the state: nothing to release on the error returns below
   cudaEventRecord(e0, r.stream);
   LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
   for (int base = 0; base < nseq; base += (int)nslots) {
@@ -1100,9 +1155,69 @@ int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_ch
   if (e != cudaSuccess) { err = std::string("linear-space kernels: ") + cudaGetErrorString(e); return 2; }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (kernel_ms) *kernel_ms = ms;
   if (launches) *launches = r.launches;
+  return 0;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ fp64 peaks
+#ifndef RELEM_HOST_EMU
+// 8 independent dependent-FMA chains per thread: enough instruction-level parallelism to keep the fp64 pipe full
+__global__ void __launch_bounds__(256) relem_fp64_dfma_kernel(double* sink, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+  for (int k = 0; k < iters; ++k) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  double v = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (v == 12345.678) sink[0] = v;   // never true: keeps the loop alive
+}
+__global__ void __launch_bounds__(256) relem_fp64_exp_kernel(double* sink, int iters, double a) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + .25, x2 = x0 + .5, x3 = x0 + .75;
+  for (int k = 0; k < iters; ++k) {
+    x0 = exp(x0 * a); x1 = exp(x1 * a); x2 = exp(x2 * a); x3 = exp(x3 * a);
+  }
+  double v = (x0 + x1) + (x2 + x3);
+  if (v == 12345.678) sink[0] = v;
+}
+#endif
+
+int lin_fp64_peak(void* stream, int sm_count, double* dfma_per_s, double* exp_per_s, std::string& err) {
+#ifdef RELEM_HOST_EMU
+  (void)stream; (void)sm_count; (void)dfma_per_s; (void)exp_per_s;
+  err = "no micro-benchmark in the emulation";
+  return 1;
+#else
+  cudaStream_t st = (cudaStream_t)stream;
+  double* sink = nullptr;
+  if (cudaMalloc(&sink, 8) != cudaSuccess) { err = "allocation failed"; return 3; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int grid = std::max(1, sm_count) * 8, threads = 256;
+  float ms = 0.f;
+  double best_f = 0., best_e = 0.;
+  for (int rep = 0; rep < 4; ++rep) {   // first repetition warms up
+    const int it_f = 20000, it_e = 1000;
+    cudaEventRecord(e0, st);
+    relem_fp64_dfma_kernel<<<grid, threads, 0, st>>>(sink, it_f, 0.999999, 1e-6);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep) best_f = std::max(best_f, (double)grid * threads * 8. * it_f / (ms * 1e-3));
+    cudaEventRecord(e0, st);
+    relem_fp64_exp_kernel<<<grid, threads, 0, st>>>(sink, it_e, 0.5);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep) best_e = std::max(best_e, (double)grid * threads * 4. * it_e / (ms * 1e-3));
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (e != cudaSuccess) { err = cudaGetErrorString(e); return 2; }
+  if (dfma_per_s) *dfma_per_s = best_f;
+  if (exp_per_s) *exp_per_s = best_e;
   return 0;
 #endif
 }

@@ -231,19 +231,29 @@ class RNAelemTrainer {
       const int ns = b.n();
       std::vector<uint8_t> skipped(ns, 0);
       V& v = part[k];
-      v.assign(nth + 5, 0.);   // fn, sum_eff, n_skipped, EN_diff[nth], EH_diff[2]
+      v.assign(nth + 6, 0.);   // fn, sum_eff, n_skipped, EN_diff[nth], EH_diff[2], number of ranks whose E-step failed
       relem_estep_out o;
       std::memset(&o, 0, sizeof o);
       o.EN_diff = v.data() + 3;
       o.skipped = skipped.data();
-      if (ns > 0)
-        dev_.ok(k, relem_estep(dev_.ctx(k), ns, b.seq.data(), b.off.data(), b.ws.data(), b.kind.data(), b.gate.data(), &o),
-                "relem_estep");
-      v[0] = o.fn; v[1] = o.sum_eff; v[2] = double(o.n_skipped);
-      v[3 + nth] = o.EH_diff[0]; v[4 + nth] = o.EH_diff[1];
-      for (int n = 0; n < ns; ++n) if (skipped[n] == 1) skipped_ids[k].push_back(b.id[n]);
+      // A rank whose E-step fails must still enter the collective (the other ranks are already waiting in it): the
+      // failure travels as one more summed element and every rank stops after the all-reduce.
+      int rc = RELEM_OK;
+      std::string why;
+      if (ns > 0) rc = relem_estep(dev_.ctx(k), ns, b.seq.data(), b.off.data(), b.ws.data(), b.kind.data(), b.gate.data(), &o);
+      if (const char* e = std::getenv("RELEM_TEST_FAIL_RANK"))   // fault injection for tests/test_host_cli.py
+        if (std::atoi(e) == k && rc == RELEM_OK) { rc = RELEM_EINVAL; why = "injected failure (RELEM_TEST_FAIL_RANK)"; }
+      if (rc != RELEM_OK && why.empty()) why = relem_last_error(dev_.ctx(k));
+      if (rc != RELEM_OK) { v.assign(nth + 6, 0.); v[5 + nth] = 1.; }
+      else {
+        v[0] = o.fn; v[1] = o.sum_eff; v[2] = double(o.n_skipped);
+        v[3 + nth] = o.EH_diff[0]; v[4 + nth] = o.EH_diff[1];
+        for (int n = 0; n < ns; ++n) if (skipped[n] == 1) skipped_ids[k].push_back(b.id[n]);
+      }
       if (nw > 1) dev_.ok(k, relem_allreduce_sum(dev_.ctx(k), v.data(), int(v.size())), "relem_allreduce_sum");
+      if (rc != RELEM_OK) die("relem: relem_estep failed on GPU", k, ":", why);
     });
+    check(part[0][5 + nth] == 0., "relem: the E-step failed on", int(part[0][5 + nth]), "GPU(s)");
     const double ms_estep = lapse();
     if (prof) {
       const char* nm[8]; float ms[8]; int nl[8];
