@@ -153,6 +153,10 @@ struct SeqView {
   const double* ws;       // [L] (global)
   int min_pair;           // smallest pair span: turn+2 = 5
   int min_multi;          // smallest multiloop span: 2*(2+turn) = 10
+  // optional (nullptr when absent): the same masks indexed by the RIGHT end of the span, bit d of row j <-> (j-d, j).
+  // With them the enumerators find interior-loop and split candidates by bit scans instead of testing every (k,l).
+  const unsigned* bpr;
+  const unsigned* lfr;
 };
 
 RDEV bool mask_bit(const unsigned* rows, int mw, int i, int d) {
@@ -169,6 +173,33 @@ RDEV bool ok_M(const SeqView& q, int i, int d) { return i > 0 && i + d < q.L && 
 RDEV bool ok_B(const SeqView& q, int i, int d) {
   return i >= 0 && d >= 0 && d <= q.W && i <= q.L && mask_bit(q.lf, q.mw, i, d);
 }
+// n (1..32) bits of a mask row starting at bit lo (lo may be negative: bits below 0 read as 0); bits beyond the row
+// read as 0
+RDEV unsigned mask_window(const unsigned* row, int mw, int lo, int n) {
+  int skip = 0;
+  if (lo < 0) { skip = -lo; lo = 0; n -= skip; }
+  if (n <= 0) return 0u;
+  int w = lo >> 5, sh = lo & 31;
+  unsigned a = w < mw ? row[w] : 0u, b = (w + 1) < mw ? row[w + 1] : 0u;
+  unsigned v = sh ? ((a >> sh) | (b << (32 - sh))) : a;
+  if (n < 32) v &= (1u << n) - 1u;
+  return skip >= 32 ? 0u : (v << skip);
+}
+#ifdef RELEM_HOST_EMU
+RDEV int bit_fls(unsigned v) { return v ? 32 - __builtin_clz(v) : 0; }       // 1-based index of the highest set bit
+RDEV unsigned bit_rev(unsigned v) {
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+  v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+  return (v >> 16) | (v << 16);
+}
+RDEV int bit_ffs(unsigned v) { return __builtin_ffs((int)v); }
+#else
+RDEV int bit_fls(unsigned v) { return 32 - __clz((int)v); }
+RDEV unsigned bit_rev(unsigned v) { return __brev(v); }
+RDEV int bit_ffs(unsigned v) { return __ffs((int)v); }
+#endif
 RDEV unsigned band_idx(const SeqView& q, int plane, int i, int d, int s) {
   return ((unsigned)plane * q.cells + (unsigned)(i * q.W1 + d)) * (unsigned)q.S + (unsigned)s;
 }

@@ -85,7 +85,7 @@ template <class V> RDEV void enum_L(const ModelView& m, const SeqView& q, int i,
     Emit em{2, -1, j - 1, j, s, s1};
     if (!v.allow(m, q, em)) continue;
     double wt = single_wt(q, sr, j - 1, dot && sr == ld_ro(h.st_r + s1));
-    v.t1(TT_L_L, band_idx(q, PL_L, i, d - 1, s1), wt, 0., 0, em, Geo{i, j - 1, s1});
+    v.t1(TT_L_L, v.bidx(q, PL_L, i, d - 1, s1), wt, 0., 0, em, Geo{i, j - 1, s1});
   }
 }
 
@@ -102,7 +102,7 @@ template <class V> RDEV void enum_P(const ModelView& m, const SeqView& q, int i,
       Emit em{1, i, j - 1, j, s, s1};
       if (!v.allow(m, q, em)) continue;
       double wt = pair_wt(m, q, s, s1, i, j - 1);
-      v.t1(TT_P_E, band_idx(q, PL_E, i + 1, d - 2, s1), wt, 0., slot, em, Geo{i + 1, j - 1, s1});
+      v.t1(TT_P_E, v.bidx(q, PL_E, i + 1, d - 2, s1), wt, 0., slot, em, Geo{i + 1, j - 1, s1});
     }
   }
   if (ok_P(q, i + 1, d - 2)) {
@@ -114,7 +114,7 @@ template <class V> RDEV void enum_P(const ModelView& m, const SeqView& q, int i,
         Emit em{1, i, j - 1, j, s, s1};
         if (!v.allow(m, q, em)) continue;
         double wt = pair_wt(m, q, s, s1, i, j - 1);
-        v.t1(TT_P_P, band_idx(q, PL_P, i + 1, d - 2, s1), d_add(wt, lt), tsc, slot, em, Geo{i + 1, j - 1, s1});
+        v.t1(TT_P_P, v.bidx(q, PL_P, i + 1, d - 2, s1), d_add(wt, lt), tsc, slot, em, Geo{i + 1, j - 1, s1});
       }
     }
   }
@@ -126,11 +126,35 @@ template <class V> RDEV void enum_B(const ModelView& m, const SeqView& q, int i,
   int j = i + d;
   int a0 = ld_ro(h.split_off + s), a1 = ld_ro(h.split_off + s + 1);
   Emit em{0, -1, -1, j, s, s};
+  if (a0 == a1) return;
+  if (q.lfr) {
+    // same visiting order (k ascending), candidates found 32 at a time: bit u of row i of the left mask AND bit d-u of
+    // row j of the right-indexed left mask
+    const unsigned* ri = q.lf + i * q.mw;
+    const unsigned* rj = q.lfr + j * q.mw;
+    for (int u0 = 0; u0 <= d; u0 += 32) {
+      int n = d - u0 + 1 < 32 ? d - u0 + 1 : 32;
+      unsigned a = mask_window(ri, q.mw, u0, n);
+      if (!a) continue;
+      unsigned b = bit_rev(mask_window(rj, q.mw, d - u0 - 31, 32));   // bit t <-> position d - u0 - t
+      unsigned mk = a & b;
+      while (mk) {
+        int t = bit_ffs(mk) - 1;
+        mk &= mk - 1;
+        int k = i + u0 + t;
+        for (int aa = a0; aa < a1; ++aa) {
+          int sl = ld_ro(h.split_left + aa), sr = ld_ro(h.split_right + aa);
+          v.t2(TT_B_12, v.bidx(q, PL_1, i, k - i, sl), v.bidx(q, PL_2, k, j - k, sr), 0., 0., 0, em, Geo{i, k, sl});
+        }
+      }
+    }
+    return;
+  }
   for (int k = i; k <= j; ++k) {
     if (!ok_B(q, i, k - i) || !ok_B(q, k, j - k)) continue;
     for (int a = a0; a < a1; ++a) {
       int sl = ld_ro(h.split_left + a), sr = ld_ro(h.split_right + a);
-      v.t2(TT_B_12, band_idx(q, PL_1, i, k - i, sl), band_idx(q, PL_2, k, j - k, sr), 0., 0., 0, em, Geo{i, k, sl});
+      v.t2(TT_B_12, v.bidx(q, PL_1, i, k - i, sl), v.bidx(q, PL_2, k, j - k, sr), 0., 0., 0, em, Geo{i, k, sl});
     }
   }
 }
@@ -148,14 +172,14 @@ template <class V> RDEV void enum_2(const ModelView& m, const SeqView& q, int i,
       Emit em{2, -1, j - 1, j, s, s1};
       if (!v.allow(m, q, em)) continue;
       double wt = single_wt(q, sr, j - 1, nr == '.' && sr == ld_ro(h.st_r + s1));
-      v.t1(TT_2_2, band_idx(q, PL_2, i, d - 1, s1), wt, 0., slot, em, Geo{i, j - 1, s1});
+      v.t1(TT_2_2, v.bidx(q, PL_2, i, d - 1, s1), wt, 0., slot, em, Geo{i, j - 1, s1});
     }
   }
   if (ok_P(q, i, d)) {
     double tsc = m.en.no_ene ? 0. : e_sum_ext_m(m.en, q, i, j - 1, false) + m.en.mlintern;
     if (tsc > NINF) {
       Emit em{0, -1, -1, j, s, s};
-      v.t1(TT_2_P, band_idx(q, PL_P, i, d, s), d_mul(lam, tsc), tsc, slot, em, Geo{i, j, s});
+      v.t1(TT_2_P, v.bidx(q, PL_P, i, d, s), d_mul(lam, tsc), tsc, slot, em, Geo{i, j, s});
     }
   }
 }
@@ -164,8 +188,8 @@ template <class V> RDEV void enum_2(const ModelView& m, const SeqView& q, int i,
 template <class V> RDEV void enum_1(const ModelView& m, const SeqView& q, int i, int d, int s, V& v) {
   int j = i + d;
   Emit em{0, -1, -1, j, s, s};
-  v.t1(TT_1_2, band_idx(q, PL_2, i, d, s), 0., 0., 0, em, Geo{i, j, s});
-  v.t1(TT_1_B, band_idx(q, PL_B, i, d, s), 0., 0., 0, em, Geo{i, j, s});
+  v.t1(TT_1_2, v.bidx(q, PL_2, i, d, s), 0., 0., 0, em, Geo{i, j, s});
+  v.t1(TT_1_B, v.bidx(q, PL_B, i, d, s), 0., 0., 0, em, Geo{i, j, s});
 }
 
 // ---- M(i,j,s) <- M(i+1,j,s1) | B(i,j,s)
@@ -181,12 +205,12 @@ template <class V> RDEV void enum_M(const ModelView& m, const SeqView& q, int i,
       if (!v.allow(m, q, em)) continue;
       int s1l = ld_ro(h.st_l + s1);
       double wt = single_wt(q, s1l, i, dot && sl == s1l);
-      v.t1(TT_M_M, band_idx(q, PL_M, i + 1, d - 1, s1), wt, 0., 0, em, Geo{i + 1, j, s1});
+      v.t1(TT_M_M, v.bidx(q, PL_M, i + 1, d - 1, s1), wt, 0., 0, em, Geo{i + 1, j, s1});
     }
   }
   if (ok_B(q, i, d)) {
     Emit em{0, -1, -1, j, s, s};
-    v.t1(TT_M_B, band_idx(q, PL_B, i, d, s), 0., 0., 0, em, Geo{i, j, s});
+    v.t1(TT_M_B, v.bidx(q, PL_B, i, d, s), 0., 0., 0, em, Geo{i, j, s});
   }
 }
 
@@ -198,16 +222,45 @@ template <class V> RDEV void enum_E(const ModelView& m, const SeqView& q, int i,
   Emit em{0, -1, -1, j, s, s};
   if (ok_M(q, i, d)) {
     double tsc = m.en.no_ene ? 0. : e_sum_ext_m(m.en, q, j, i - 1, false) + (m.en.mlclosing + m.en.mlintern);
-    if (tsc > NINF) v.t1(TT_E_M, band_idx(q, PL_M, i, d, s), d_mul(lam, tsc), tsc, slot, em, Geo{i, j, s});
+    if (tsc > NINF) v.t1(TT_E_M, v.bidx(q, PL_M, i, d, s), d_mul(lam, tsc), tsc, slot, em, Geo{i, j, s});
   }
   if (ld_ro(h.is_loop + s)) {
     double tsc = m.en.no_ene ? 0. : e_hairpin(m.en, q, i - 1, j);
-    if (tsc > NINF) v.t1(TT_E_H, band_idx(q, PL_L, i, d, s), d_mul(lam, tsc), tsc, slot, em, Geo{i, j, s});
+    if (tsc > NINF) v.t1(TT_E_H, v.bidx(q, PL_L, i, d, s), d_mul(lam, tsc), tsc, slot, em, Geo{i, j, s});
   }
   int a0 = ld_ro(h.quad_off + s), a1 = ld_ro(h.quad_off + s + 1);
   if (a0 == a1) return;
   int C = q.C;
   int lmin = j - C > i ? j - C : i;
+  if (q.bpr) {
+    // same visiting order (l descending, k ascending), inner pairs found by scanning row l of the right-indexed pair
+    // mask: bit dd <-> pair (l-dd, l), k ascending = dd descending
+    for (int l = j; l >= lmin; --l) {
+      int kmax = i + C - (j - l);
+      if (kmax > l) kmax = l;
+      const unsigned* rl = q.bpr + l * q.mw;
+      int dlo = l - kmax;
+      for (int hi = l - i; hi >= dlo; hi -= 32) {
+        int lo = hi - 31 > dlo ? hi - 31 : dlo;
+        unsigned mk = mask_window(rl, q.mw, lo, hi - lo + 1);
+        while (mk) {
+          int t = bit_fls(mk) - 1;
+          mk &= ~(1u << t);
+          int k = l - (lo + t);
+          if (k == i && l == j) continue;
+          double tsc = m.en.no_ene ? 0. : e_loop(m.en, q, i - 1, j, k, l - 1);
+          if (!(tsc > NINF)) continue;
+          double lt = d_mul(lam, tsc);
+          for (int a = a0; a < a1; ++a) {
+            int s1 = ld_ro(h.quad_s1 + a), s2 = ld_ro(h.quad_s2 + a), s3 = ld_ro(h.quad_s3 + a);
+            v.t3(TT_E_P, v.bidx(q, PL_P, k, l - k, s1), v.bidx(q, PL_L, i, k - i, s2),
+                 v.bidx(q, PL_L, l, j - l, s3), lt, tsc, slot, em, Geo{k, l, s1});
+          }
+        }
+      }
+    }
+    return;
+  }
   for (int l = j; l >= lmin; --l) {
     int kmax = i + C - (j - l);
     if (kmax > l) kmax = l;
@@ -219,8 +272,8 @@ template <class V> RDEV void enum_E(const ModelView& m, const SeqView& q, int i,
       double lt = d_mul(lam, tsc);
       for (int a = a0; a < a1; ++a) {
         int s1 = ld_ro(h.quad_s1 + a), s2 = ld_ro(h.quad_s2 + a), s3 = ld_ro(h.quad_s3 + a);
-        v.t3(TT_E_P, band_idx(q, PL_P, k, l - k, s1), band_idx(q, PL_L, i, k - i, s2),
-             band_idx(q, PL_L, l, j - l, s3), lt, tsc, slot, em, Geo{k, l, s1});
+        v.t3(TT_E_P, v.bidx(q, PL_P, k, l - k, s1), v.bidx(q, PL_L, i, k - i, s2),
+             v.bidx(q, PL_L, l, j - l, s3), lt, tsc, slot, em, Geo{k, l, s1});
       }
     }
   }
@@ -240,7 +293,7 @@ template <class V> RDEV void enum_O(const ModelView& m, const SeqView& q, int j,
     double lt = d_mul(lam, tsc);
     for (int a = a0; a < a1; ++a) {
       int sl = ld_ro(h.split_left + a), sr = ld_ro(h.split_right + a);
-      v.o2(TT_O_OP, (unsigned)(i * q.S + sl), band_idx(q, PL_P, i, j - i, sr), lt, tsc, slot, em0, Geo{i, j, sr});
+      v.o2(TT_O_OP, (unsigned)(i * q.S + sl), v.bidx(q, PL_P, i, j - i, sr), lt, tsc, slot, em0, Geo{i, j, sr});
     }
   }
   if (j > 0) {

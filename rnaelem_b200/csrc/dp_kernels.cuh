@@ -8,6 +8,7 @@
 #define RELEM_DP_KERNELS_CUH
 #include "dp_batch.hpp"
 #include "dp_warp.cuh"
+#include "dp_vit.cuh"
 
 namespace relem {
 namespace dp {
@@ -76,7 +77,7 @@ RDEV double cta_prepare(const ModelView& nullm, const ModelView& m, const BatchV
   int W = L < m.en.max_span ? L : m.en.max_span;
   int C = W - 7 < m.en.max_iloop ? W - 7 : m.en.max_iloop;
   q.L = L; q.W = W; q.C = C; q.W1 = W + 1; q.cells = (unsigned)(L + 1) * (unsigned)(W + 1);
-  q.mw = lay.mw; q.min_pair = 5; q.min_multi = 10;
+  q.mw = lay.mw; q.min_pair = 5; q.min_multi = 10; q.bpr = nullptr; q.lfr = nullptr;
   q.x = sm.x; q.bp = sm.bp; q.lf = sm.lf; q.sp3 = sm.sp3; q.sp4 = sm.sp4; q.sp6 = sm.sp6;
   q.ws = b.ws + o;
   for (int t = CTA_TID; t < L; t += CTA_NTH) sm.x[t] = b.seq[o + t];
@@ -368,15 +369,6 @@ RDEV int last_max_index(const double* v, int n) {
   return s;
 }
 
-RDEV int child_plane_of(int tt) {
-  switch (tt) {
-    case TT_E_H: return PL_L; case TT_P_E: return PL_E; case TT_P_P: return PL_P; case TT_O_O: return 7;
-    case TT_O_OP: return PL_P; case TT_E_P: return PL_P; case TT_E_M: return PL_M; case TT_M_M: return PL_M;
-    case TT_M_B: return PL_B; case TT_B_12: return PL_1; case TT_1_B: return PL_B; case TT_1_2: return PL_2;
-    case TT_2_2: return PL_2; case TT_2_P: return PL_P; case TT_L_L: return PL_L;
-  }
-  return -1;
-}
 
 // RNAelemScanDP::trace_back (motif_scanner.hpp:262-362), one thread
 RDEV void trace_back(const ModelView& m, const SeqView& q, const unsigned long long* trace,
@@ -556,6 +548,10 @@ RELEM_KERNEL relem_viterbi_kernel(ModelView m, BatchView b, SlotLayout lay, doub
   double* slot = scratch + (unsigned long long)RELEM_BLOCK_IDX * lay.stride;
   const int S = m.h.S;
   const DevHMM& h = m.h;
+  // background states of cells outside the motif region (StartEndConstraint, dp_enum.cuh)
+  int s_bgM = -1;
+  for (int s = 0; s < S; ++s)
+    if (ld_ro(h.st_l + s) == h.M - 1 && ld_ro(h.st_r + s) == h.M - 1) s_bgM = s;
   for (;;) {
     int qi = claim(queue, (int*)(sm.red + 40));
     if (qi >= em.count) break;
@@ -573,26 +569,29 @@ RELEM_KERNEL relem_viterbi_kernel(ModelView m, BatchView b, SlotLayout lay, doub
     q.ws = b.ws + o;
     for (int t = CTA_TID; t < L; t += CTA_NTH) sm.x[t] = b.seq[o + t];
     if (CTA_TID == 0) sm.x[L] = 0;
+    // the four masks the linear-space passes left in the slot header: pairs and left-ends by left end (copied to
+    // shared memory: every gate test reads them) and by right end (read in place: candidate scans only)
     const unsigned* g = (const unsigned*)(em.scratch + (unsigned long long)qi * em.stride + em.masks_off);
     for (int t = CTA_TID; t < (L + 1) * lay.mw; t += CTA_NTH) { sm.bp[t] = g[t]; sm.lf[t] = g[em.mask_words + t]; }
+    q.bpr = g + 2 * (size_t)em.mask_words; q.lfr = g + 3 * (size_t)em.mask_words;
     CTA_SYNC();
     cta_special_hairpins(m.en, sm.x, L, sm.sp3, sm.sp4, sm.sp6);
     double* emit0 = slot + lay.emit0; double* emitT = slot + lay.emitT;
     q.emit0 = emit0; q.emitT = emitT;
     cta_emit_tables(m, q, emit0, emitT);
+    for (int t = CTA_TID; t < L; t += CTA_NTH) { out.psihat[o + t] = 0; out.rss[o + t] = ' '; }
     CTA_SYNC();
     double* tab = slot + lay.tabA; double* otab = slot + lay.otab;
     StartEndConstraint se; se.ys = out.Ys[n]; se.ye = out.Ye[n];
-    unsigned long long* trace = (unsigned long long*)(slot + lay.Q0);
-    unsigned long long* otrace = (unsigned long long*)(slot + lay.QO0);
-    cta_inside<true, StartEndConstraint>(m, q, tab, otab, trace, otrace, se);
-    for (int t = CTA_TID; t < L; t += CTA_NTH) { out.psihat[o + t] = 0; out.rss[o + t] = ' '; }
-    CTA_SYNC();
+    VitRegion rg;
+    rg.ys = se.ys; rg.ye = se.ye; rg.s_bg0 = h.s00; rg.s_bgM = s_bgM;
+    rg.on = h.s00 >= 0 && s_bgM >= 0 && se.ys >= 0 && se.ye >= se.ys;
+    cta_viterbi_forward(m, q, tab, otab, se, rg);
     if (CTA_TID == 0) {
       double a = h.s0M2 >= 0 ? otab[L * S + h.s0M2] : NINF;
       double c = h.s0M1 >= 0 ? otab[L * S + h.s0M1] : NINF;
       int s0 = (a < c) ? h.s0M1 : h.s0M2;
-      if (s0 >= 0) trace_back(m, q, trace, otrace, n2s, (int*)(slot + lay.stack), s0, out.psihat + o, out.rss + o);
+      if (s0 >= 0) vit_trace_back(m, q, tab, otab, se, rg, n2s, (int*)(slot + lay.stack), s0, out.psihat + o, out.rss + o);
     }
     CTA_SYNC();
   }

@@ -29,6 +29,7 @@ RDEV double lse2(double x, double y) {
 
 // ------------------------------------------------------------------------------------------------ visitors
 template <class CON> struct SumV {
+  RDEV unsigned bidx(const SeqView& q, int plane, int i, int d, int s) const { return band_idx(q, plane, i, d, s); }
   const double* tab;
   const double* otab;
   CON con;
@@ -57,6 +58,7 @@ RDEV unsigned long long pack_trace(int tt, const Geo& g) {
 }
 #define RELEM_NO_TRACE 0xFFFFFFFFFFFFFFFFull
 template <class CON> struct MaxV {
+  RDEV unsigned bidx(const SeqView& q, int plane, int i, int d, int s) const { return band_idx(q, plane, i, d, s); }
   const double* tab;
   const double* otab;
   CON con;
@@ -109,6 +111,7 @@ RDEV int plane_of_same_cell(int tt) {
 }
 
 template <int NCH, int HOOK, class CON> struct ScatV {
+  RDEV unsigned bidx(const SeqView& q, int plane, int i, int d, int s) const { return band_idx(q, plane, i, d, s); }
   const double* tab;
   const double* otab;
   double* Q[NCH];

@@ -889,7 +889,12 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
 #else
     ll.stream = nullptr;
 #endif
-    struct VitCtx { relem_ctx* c; ModelView m; BatchView bv; Launch* L; ScanOut so; } vc{c, m, bv, &L, so};
+    struct VitCtx {
+      relem_ctx* c; ModelView m; BatchView bv; Launch* L; ScanOut so;
+#ifndef RELEM_HOST_EMU
+      std::vector<cudaEvent_t> ev;   // one pair per chunk around the Viterbi launch
+#endif
+    } vc{c, m, bv, &L, so};
     auto after_chunk = [](void* user, const lin::LinChunkView& cv) -> int {
       VitCtx& v = *(VitCtx*)user;
       ExtMasks em;
@@ -905,19 +910,37 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
 #else
       cudaStream_t st = (cudaStream_t)cv.stream;
       if (cudaMemsetAsync(c->d_queue.p, 0, sizeof(int), st) != cudaSuccess) return 1;
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      v.ev.push_back(e0); v.ev.push_back(e1);
+      cudaEventRecord(e0, st);
       relem_viterbi_kernel<<<std::min(v.L->nslots, cv.count), RELEM_CTA_THREADS, v.L->lay.sm_total, st>>>(
           v.m, v.bv, v.L->lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), c->d_n2s.as<int>(), v.so, em,
           c->d_flag.as<unsigned char>());
+      cudaEventRecord(e1, st);
       return cudaGetLastError() == cudaSuccess ? 0 : 1;
 #endif
     };
     float ms = 0.f; int nl = 0; std::string lerr;
     int lrc = lin::lin_scan_launch(c->lin, ll, after_chunk, &vc, &ms, &nl, lerr);
+    float vit_ms = 0.f;
+    int vit_n = 0;
+#ifndef RELEM_HOST_EMU
+    if (lrc == 0)
+      for (size_t k = 0; k + 1 < vc.ev.size(); k += 2) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, vc.ev[k], vc.ev[k + 1]) == cudaSuccess) { vit_ms += t; ++vit_n; }
+      }
+    for (cudaEvent_t e : vc.ev) cudaEventDestroy(e);
+#endif
     if (lrc == 1) {
       use_lin = false;
     } else {
       if (lrc) return fail(c, lrc == 3 ? RELEM_ENOMEM : RELEM_ECUDA, "linear-space scan: " + lerr);
-      c->timing.push_back(TimingEntry{"relem_scan_lin_kernels", ms, nl});
+      // the chunk loop's bracket covers the posterior passes AND the Viterbi launches; the second entry is the
+      // Viterbi share of it (0 launches: already counted in the first)
+      c->timing.push_back(TimingEntry{"relem_scan_lin_kernels", ms, nl + vit_n});
+      c->timing.push_back(TimingEntry{"relem_viterbi_kernel (share of the above)", vit_ms, -vit_n});
       std::vector<unsigned char> flags(nseq);
       if (!Dev::d2h(flags.data(), c->d_flag.p, nseq)) return fail(c, RELEM_ECUDA, "flag copy failed");
       std::vector<int> redo;

@@ -156,7 +156,7 @@ RDEV LinCtx& lin_attach(const LinKArgs& a, unsigned char* smem_raw, int sk, doub
     const int C = W - 7 < LC.en.max_iloop ? W - 7 : LC.en.max_iloop;
     SeqView& q = c.q;
     q.L = L; q.W = W; q.C = C; q.W1 = W + 1; q.S = LC.h.S; q.cells = (unsigned)(L + 1) * (unsigned)(W + 1);
-    q.mw = lay.mw; q.min_pair = 5; q.min_multi = 10;
+    q.mw = lay.mw; q.min_pair = 5; q.min_multi = 10; q.bpr = nullptr; q.lfr = nullptr;
     unsigned char* by = (unsigned char*)(slot + lay.bytes);
     q.x = by;
     q.sp3 = (signed char*)(by + (lay.Lmax + 2));

@@ -9,6 +9,7 @@ tests/golden/cli/ are committed and travel to the GPU box.
 import json
 import os
 import subprocess
+import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
@@ -34,6 +35,13 @@ CASES = {
                                                "--lambda-init", "0.4"], None),
     # scan of 200-nt reads with a model FILE: same parameter bits on both sides -> Viterbi strings exact
     "synth_scan": ("scan", "synth.fq", [], "synth_adam"),
+    # --no-shuffle: positives only, L-BFGS-B (optimizer.hpp:175-2791) instead of Adam; the sub-command-less form also
+    # writes the model and scans.  Only the reference's own optimizer can run this (the patched reference binary
+    # oracle/_ref/RNAelem_gpu of tests/test_reference_dropin.py); the shipped command line refuses --no-shuffle.
+    "synth_lbfgsb": (None, "synth.fq", ["-m", "((.*.))", "--no-shuffle", "--max-iter", "6", "--batch-size", "-1",
+                                        "--lambda-init", "0.7"], None),
+    "ragged_lbfgsb": ("train", "ragged.fq", ["-m", "(.*)", "--no-shuffle", "--max-iter", "5", "--batch-size", "-1",
+                                             "--lambda-init", "0.3"], None),
     # shuffled negatives only
     "genneg_k2": ("gen-neg", "ragged.fq", ["-i", "3"], None),
     "genneg_k3": ("gen-neg", "synth.fq", ["-i", "2", "--kmer-shuf", "3"], None),
@@ -44,7 +52,13 @@ CASES = {
 def main():
     assert os.path.exists(REF), "build oracle/_ref first (make -C oracle ref)"
     manifest = {}
+    only = set(sys.argv[1:])
+    mp = os.path.join(OUT, "manifest.json")
+    if only and os.path.exists(mp):
+        manifest = json.load(open(mp))
     for name, (sub, fq, extra, model_case) in CASES.items():
+        if only and name not in only:
+            continue
         d = os.path.join(OUT, name)
         os.makedirs(d, exist_ok=True)
         cmd = [REF] + ([sub] if sub else []) + ["-f", os.path.join(HERE, "_tmp", fq), "-t", "1"] + extra
