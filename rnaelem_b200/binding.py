@@ -11,7 +11,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "librelem.so")
+    # RELEM_LIBRARY: an A/B build of the same CUDA sources with other compile-time switches (tools/build_variant.sh);
+    # always a CUDA build of this repository's kernels, never a CPU path
+    return os.environ.get("RELEM_LIBRARY") or os.path.join(_HERE, "librelem.so")
 
 
 class RelemError(RuntimeError):

@@ -14,6 +14,7 @@ namespace relem {
 namespace dp {
 
 #define RELEM_CTA_THREADS 128
+#define RELEM_VIT_THREADS 256   // Viterbi kernel: 8 warps share one sequence
 
 // per-slot scratch, offsets in doubles from the slot base
 struct SlotLayout {
@@ -23,6 +24,7 @@ struct SlotLayout {
   // dynamic shared memory carve-up (byte offsets)
   int sm_x, sm_sp3, sm_sp4, sm_sp6, sm_bp, sm_lf, sm_bp2, sm_en, sm_pys, sm_pyi, sm_pye, sm_red, sm_ctr, sm_warp, warp_bytes,
       sm_total;
+  int sm_vit_ctr, sm_vit_warp, vit_warp_bytes, sm_total_vit, vit_n_max;   // Viterbi kernel: see make_layout
 };
 
 struct BppOut {
@@ -539,7 +541,12 @@ struct ExtMasks {
   int mask_words;                  // words per mask
   int base, count;                 // chunk = sequences order[base .. base+count), slot k <-> base+k
 };
-RELEM_KERNEL relem_viterbi_kernel(ModelView m, BatchView b, SlotLayout lay, double* scratch, int* queue, const int* n2s,
+#ifdef RELEM_HOST_EMU
+#define RELEM_VIT_KERNEL inline void
+#else
+#define RELEM_VIT_KERNEL __global__ void __launch_bounds__(RELEM_VIT_THREADS, 2)
+#endif
+RELEM_VIT_KERNEL relem_viterbi_kernel(ModelView m, BatchView b, SlotLayout lay, double* scratch, int* queue, const int* n2s,
                                   ScanOut out, ExtMasks em, const unsigned char* flag RELEM_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -586,7 +593,8 @@ RELEM_KERNEL relem_viterbi_kernel(ModelView m, BatchView b, SlotLayout lay, doub
     VitRegion rg;
     rg.ys = se.ys; rg.ye = se.ye; rg.s_bg0 = h.s00; rg.s_bgM = s_bgM;
     rg.on = h.s00 >= 0 && s_bgM >= 0 && se.ys >= 0 && se.ye >= se.ys;
-    cta_viterbi_forward(m, q, tab, otab, se, rg);
+    VitWarp vw = vit_warp_carve(smem_raw + lay.sm_vit_warp + warp_id() * lay.vit_warp_bytes, S, lay.vit_n_max);
+    cta_viterbi_forward(m, q, tab, otab, se, rg, vw, (int*)(smem_raw + lay.sm_vit_ctr));
     if (CTA_TID == 0) {
       double a = h.s0M2 >= 0 ? otab[L * S + h.s0M2] : NINF;
       double c = h.s0M1 >= 0 ? otab[L * S + h.s0M1] : NINF;

@@ -8,7 +8,8 @@ namespace dp {
 
 // nch: posterior channels kept at once (2 for the E-step, 1 for scan / bpp); with_coupled = false sizes the
 // scratch for the energy-only filter alone.
-inline SlotLayout make_layout(int Lmax, int max_span, int S, int M, int n_theta, int nch, bool with_coupled) {
+inline SlotLayout make_layout(int Lmax, int max_span, int S, int M, int n_theta, int nch, bool with_coupled,
+                              int n_list_max = 0) {
   SlotLayout lay;
   std::memset(&lay, 0, sizeof(lay));
   int Wmax = Lmax < max_span ? Lmax : max_span;
@@ -47,6 +48,15 @@ inline SlotLayout make_layout(int Lmax, int max_span, int S, int M, int n_theta,
   lay.warp_bytes = warp_sm_bytes(S, Wmax);
   lay.sm_warp = sm(lay.warp_bytes * (RELEM_CTA_THREADS / 32));
   lay.sm_total = b;
+  // the Viterbi kernel (dp_vit.cuh) has its own tail: a per-diagonal work counter and one VitWarp slice per warp, placed
+  // where the log-space kernels keep their warp slices
+  int bv = lay.sm_warp;
+  auto smv = [&](int bytes) { int r = bv; bv += (bytes + 15) & ~15; return r; };
+  lay.sm_vit_ctr = smv((Wmax + 2) * 4);
+  lay.vit_n_max = n_list_max > S ? n_list_max : S;
+  lay.vit_warp_bytes = vit_warp_bytes(S, Wmax, lay.vit_n_max);
+  lay.sm_vit_warp = smv(lay.vit_warp_bytes * (RELEM_VIT_THREADS / 32));
+  lay.sm_total_vit = bv;
   return lay;
 }
 

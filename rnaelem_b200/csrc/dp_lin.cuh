@@ -51,6 +51,16 @@ using namespace relem::dp;
 
 #define LIN_CAP 64  // structural candidates buffered per warp before the list lanes consume them
 
+// Interior loops in the outside pass.  1 (default): SCATTER -- once E(i,j) is final, the warp that owns it walks its
+// inner pairs once and pushes the loop posteriors down to the inner pair P(k,l) and to the two unpaired flanks L(i,k),
+// L(l,j) with fp64 RED operations (the reference's direction, motif_trainer.hpp:408-456); the loop energy is evaluated
+// twice per E-step (inside E, outside E).  0: GATHER -- every child collects from its enclosing loops in three kernels
+// of its own (outside P part 2, outside L parts 2 / 3): no atomics on tables, bit-reproducible, but the loop energy is
+// evaluated four times and the enclosing-pair scans are repeated per child.  Measured: profiles/r2_scatter_ab.md.
+#ifndef LIN_SCATTER_ILOOP
+#define LIN_SCATTER_ILOOP 1
+#endif
+
 struct LinEnergyScalars {  // linear-domain copies of the scalar energy terms
   double term_au, mlintern, mlclosing;
 };
@@ -1170,7 +1180,9 @@ RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, boo
         double v = seg_sum(w.partA + ch * NM, h.pT_off, s);
         cE[ch * S + s] = v;
         t.bEl[ch * t.bch + il + s] = v;
-        t.bEr[ch * t.bch + ir + s] = v;
+#if !LIN_SCATTER_ILOOP
+        t.bEr[ch * t.bch + ir + s] = v;   // only the right-flank gather reads E by its right end
+#endif
       }
     w_sync();
   }
@@ -1527,7 +1539,8 @@ RDEV void lin_out_P(const LinCtx& c, const CTabs& t, int i, int d, bool gB, Warp
       for (int ch = 0; ch < NCH; ++ch) cP[ch * S + s] += seg_sum(w.partA + ch * NM, h.qP_off, s);
     w_sync();
   }
-  if (PART == 2) {
+  if (PART == 2 || (LIN_SCATTER_ILOOP && PART == 1)) {
+    // scatter mode: the enclosing loops have already added their share (lin_out_ES at larger spans) to the zeroed entry
     for (int s = lane; s < S; s += WARP_N)
       for (int ch = 0; ch < NCH; ++ch) t.bP[ch * t.bch + il + s] += cP[ch * S + s];
   } else {
@@ -1677,11 +1690,62 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
       for (int s = lane; s < S; s += WARP_N)
         for (int ch = 0; ch < NCH; ++ch) t.bL[ch * t.bch + il + s] += cL[ch * S + s];
   } else if (d >= 1) {
-    for (int s = lane; s < S; s += WARP_N)
-      for (int ch = 0; ch < NCH; ++ch) t.bL[ch * t.bch + il + s] = cL[ch * S + s];
+    if (LIN_SCATTER_ILOOP && PART == 1 && d <= c.Ceff && h.n_quad > 0) {
+      // a possible flank: the loops it flanks have already added their share (lin_out_ES) to the zeroed entry
+      for (int s = lane; s < S; s += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) t.bL[ch * t.bch + il + s] += cL[ch * S + s];
+    } else {
+      for (int s = lane; s < S; s += WARP_N)
+        for (int ch = 0; ch < NCH; ++ch) t.bL[ch * t.bch + il + s] = cL[ch * S + s];
+    }
   }
   w_sync();
 }
+
+// ---- outside, phase ES (cells enclosed by a pair; scatter mode): E(i,j,s) <- P(k,l,s1) L(i,k,s2) L(l,j,s3).
+// With b^E(i,j,.) final, every (inner pair, quad) term t = b^E f a^P a^L a^L is a transition posterior; the outside values
+// of its children are t divided by the child's own inside value, i.e. the product of the other factors.
+template <int NCH, int MODE = 0>
+RDEV void lin_out_ES(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w, EhAcc<NCH>& eh) {
+  const LinHMM& h = LC.h;
+  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
+  const int S = q.S, j = i + d, lane = lane_id();
+  if (h.n_quad <= 0) return;
+  const unsigned il = cidx(q, i, d);
+  const unsigned r0 = cidx(q, i, 0);
+  const double* rL = t.aLl + r0;
+  const double* rR = t.aLr + cidx(q, j, 0);
+  walk_inner(c, i, d, w, [&](int n) {
+    for (int a = lane; a < h.n_quad; a += WARP_N) {
+      const int s = ld_ro(h.q_tgt + a), s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a), s3 = ld_ro(h.q_s3 + a);
+      const int sl = ld_ro(h.slot + s);
+      const double* bf = sl ? w.bf1 : w.bf0;
+      double be[NCH];
+      bool any = false;
+      for (int ch = 0; ch < NCH; ++ch) { be[ch] = t.bEl[ch * t.bch + il + s]; any = any || be[ch] != 0.; }
+      if (!any) continue;
+      for (int pp = 0; pp < n; ++pp) {
+        const int k = w.bi[pp], l = w.bj[pp];
+        const double f = bf[pp];
+        if (f == 0.) continue;
+        const double ap = t.aP[cidx(q, l, l - k) + s1];
+        const double al = rL[(unsigned)(k - i) * S + s2], ar = rR[(unsigned)(j - l) * S + s3];
+        const double lr = al * ar, tsc = w.bt[pp];
+        const unsigned ip = cidx(q, k, l - k) + s1, ifl = r0 + (unsigned)(k - i) * S + s2, ifr = cidx(q, l, j - l) + s3;
+        for (int ch = 0; ch < NCH; ++ch) {
+          const double x = be[ch] * f;
+          if (x == 0.) continue;
+          const double xp = x * ap;
+          if (lr != 0.) red_add(t.bP + ch * t.bch + ip, x * lr);
+          if (k > i && xp * ar != 0.) red_add(t.bL + ch * t.bch + ifl, xp * ar);
+          if (l < j && xp * al != 0.) red_add(t.bL + ch * t.bch + ifr, xp * al);
+          eh.add(ch, sl, tsc * (xp * lr));
+        }
+      }
+    }
+  });
+}
+
 
 // one diagonal of the outside pass, phase-major over the warp's cells
 template <int NCH> RDEV void lin_outside_diag(const LinCtx& c, const CTabs& t, int d, WarpLin& w, EhAcc<NCH>& eh) {

@@ -104,8 +104,8 @@ template <class CON> struct VitTraceV : VitBase<CON> {
   }
 };
 
-// the same-cell chain L, P, B, 2, 1, M, E of one (cell, state); same-cell reads (2 <- P, 1 <- 2 B, M <- B, E <- M L)
-// are entries this thread has just written
+// the same-cell chain L, P, B, 2, 1, M, E of one (cell, state) through the reference-order enumerators: used for the
+// single-state cells outside the motif region, one thread per cell
 template <class CON>
 RDEV void vit_cell_state(const ModelView& m, const SeqView& q, double* tab, const double* otab, const CON& con,
                          const VitRegion& rg, int i, int d, int s) {
@@ -129,31 +129,287 @@ RDEV void vit_cell_state(const ModelView& m, const SeqView& q, double* tab, cons
   if (gE) { v.init(); enum_E(m, q, i, d, s, v); tab[band_idx(q, PL_E, i, d, s)] = v.best; }
 }
 
-// forward pass of one sequence by one CTA; one barrier per diagonal
+// ---- cells that overlap the motif region (S states): one warp per cell, the 32 lanes over the ENTRIES of the flattened
+// transition lists (right / left / pair transitions, splits, quads: DevHMM, grouped by parent state), structural
+// candidates (split points, inner pairs) found once per warp from the bit masks.  Every candidate value is formed with
+// the same explicit IEEE adds, in the same association, as MaxV forms it (dp_pass.cuh); max is exact, so the stored
+// values are the reference's bit for bit although the order of evaluation is not.
+#define RELEM_VIT_CAP 64
+struct VitWarp {
+  double* part;   // [n_max] per-entry maxima
+  double* curB;   // [S] B of the cell
+  double* bt;     // [CAP] loop energies of the buffered inner pairs
+  int *bi, *bj;   // [CAP] buffered inner pairs (k, l)
+  int* kbuf;      // [W+2] split points
+};
+RHD int vit_warp_bytes(int S, int Wmax, int n_max) {
+  int n = (n_max + S + RELEM_VIT_CAP) * 8 + (2 * RELEM_VIT_CAP + Wmax + 4) * 4;
+  return (n + 15) & ~15;
+}
+RDEV VitWarp vit_warp_carve(unsigned char* base, int S, int n_max) {
+  VitWarp w;
+  double* p = (double*)base;
+  w.part = p; p += n_max;
+  w.curB = p; p += S;
+  w.bt = p; p += RELEM_VIT_CAP;
+  int* ip = (int*)p;
+  w.bi = ip; ip += RELEM_VIT_CAP;
+  w.bj = ip; ip += RELEM_VIT_CAP;
+  w.kbuf = ip;
+  return w;
+}
+RDEV double vmax(double a, double b) { return a < b ? b : a; }
+RDEV double vit_seg_max(const double* part, const int* off, int s) {
+  const int a = ld_ro(off + s), n = ld_ro(off + s + 1) - a;
+  double v = NINF;
+  for (int k = 0; k < n; ++k) v = vmax(v, part[a + k]);
+  return v;
+}
+// which single state a child cell keeps (-1: all of them)
+RDEV int vit_only(const VitRegion& rg, int i, int d) {
+  if (!rg.on || d == 0) return -1;
+  if (i + d < rg.ys) return rg.s_bg0;
+  if (i > rg.ye + 1) return rg.s_bgM;
+  return -1;
+}
+RDEV double vit_ld(const SeqView& q, const double* tab, int plane, int i, int d, int s, int only) {
+  return (only < 0 || s == only) ? tab[band_idx(q, plane, i, d, s)] : NINF;
+}
+
+template <class CON>
+RDEV void vit_full_cell(const ModelView& m, const SeqView& q, double* tab, const CON& con, const VitRegion& rg, int i, int d,
+                        VitWarp& w) {
+  const DevHMM& h = m.h;
+  const int S = q.S, j = i + d, lane = lane_id();
+  const bool ne = m.en.no_ene != 0;
+  if (d == 0) {
+    for (int s = lane; s < S; s += WARP_N) tab[band_idx(q, PL_L, i, 0, s)] = (ld_ro(h.st_l + s) == ld_ro(h.st_r + s)) ? 0. : NINF;
+    return;
+  }
+  // ---- L(i,j,s) <- L(i,j-1,s1) emitting x[j-1]     (enum_L)
+  {
+    const int on1 = vit_only(rg, i, d - 1);
+    for (int a = lane; a < h.n_right; a += WARP_N) {
+      const int s = ld_ro(h.right_tgt + a), s1 = ld_ro(h.right_idx + a);
+      double v = NINF;
+      if (ld_ro(h.is_loop + s)) {
+        Emit em{2, -1, j - 1, j, s, s1};
+        if (con.ok(m, q, em)) {
+          const int sr = ld_ro(h.st_r + s);
+          const double wt = single_wt(q, sr, j - 1, ld_ro(h.node + sr) == '.' && sr == ld_ro(h.st_r + s1));
+          v = d_add(vit_ld(q, tab, PL_L, i, d - 1, s1, on1), wt);
+        }
+      }
+      w.part[a] = v;
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) tab[band_idx(q, PL_L, i, d, s)] = vit_seg_max(w.part, h.right_off, s);
+    w_sync();
+  }
+  if (d < q.min_pair - 2) return;
+  const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d), gE = ok_E(q, i, d);
+  // ---- P(i,j,s) <- E(i+1,j-1,s1) | P(i+1,j-1,s1)    (enum_P)
+  if (gP) {
+    const bool cE = ok_E(q, i + 1, d - 2), cP = ok_P(q, i + 1, d - 2);
+    double tsc = 0.;
+    bool cPP = cP;
+    if (cP && !ne) { tsc = e_loop(m.en, q, i, j - 1, i + 1, j - 2); cPP = tsc > NINF; }
+    const int on1 = vit_only(rg, i + 1, d - 2);
+    for (int a = lane; a < h.n_pair; a += WARP_N) {
+      const int s = ld_ro(h.pair_tgt + a), s1 = ld_ro(h.pair_idx + a);
+      double v = NINF;
+      Emit em{1, i, j - 1, j, s, s1};
+      if ((cE || cPP) && con.ok(m, q, em)) {
+        int slot; const double lam = lam_of(m, s, slot);
+        const double wt = pair_wt(m, q, s, s1, i, j - 1);
+        if (cE) v = vmax(v, d_add(vit_ld(q, tab, PL_E, i + 1, d - 2, s1, on1), wt));
+        if (cPP) v = vmax(v, d_add(vit_ld(q, tab, PL_P, i + 1, d - 2, s1, on1), d_add(wt, d_mul(lam, tsc))));
+      }
+      w.part[a] = v;
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) tab[band_idx(q, PL_P, i, d, s)] = vit_seg_max(w.part, h.pair_off, s);
+    w_sync();
+  }
+  if (gB) {
+    // ---- B(i,j,s) <- 1(i,k,sl) 2(k,j,sr)              (enum_B)
+    int nk = 0;
+    {
+      const unsigned* ri = q.lf + i * q.mw;
+      for (int u0 = 0; u0 <= d; u0 += WARP_N) {
+        const int u = u0 + lane;
+        const bool ok = u <= d && ((ri[u >> 5] >> (u & 31)) & 1u) && ok_B(q, i + u, d - u);
+        const unsigned bal = w_ballot(ok);
+        if (ok) w.kbuf[nk + w_popc(bal & lanemask_lt())] = u;
+        nk += w_popc(bal);
+      }
+      w_sync();
+    }
+    for (int a = lane; a < h.n_split; a += WARP_N) {
+      const int sl = ld_ro(h.split_left + a), sr = ld_ro(h.split_right + a);
+      double v = NINF;
+      for (int t = 0; t < nk; ++t) {
+        const int u = w.kbuf[t];
+        const int o1 = vit_only(rg, i, u), o2 = vit_only(rg, i + u, d - u);
+        v = vmax(v, d_add(vit_ld(q, tab, PL_1, i, u, sl, o1), d_add(vit_ld(q, tab, PL_2, i + u, d - u, sr, o2), 0.)));
+      }
+      w.part[a] = v;
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) {
+      const double x = vit_seg_max(w.part, h.split_off, s);
+      w.curB[s] = x;
+      tab[band_idx(q, PL_B, i, d, s)] = x;
+    }
+    w_sync();
+    // ---- 2(i,j,s) <- 2(i,j-1,s1) emitting x[j-1] | P(i,j,s);   1(i,j,s) <- 2(i,j,s) | B(i,j,s)     (enum_2, enum_1)
+    const bool ok2 = ok_B(q, i, d - 1);
+    const int on2 = vit_only(rg, i, d - 1);
+    for (int a = lane; a < h.n_right; a += WARP_N) {
+      const int s = ld_ro(h.right_tgt + a), s1 = ld_ro(h.right_idx + a);
+      double v = NINF;
+      Emit em{2, -1, j - 1, j, s, s1};
+      if (ok2 && con.ok(m, q, em)) {
+        const int sr = ld_ro(h.st_r + s);
+        const double wt = single_wt(q, sr, j - 1, ld_ro(h.node + sr) == '.' && sr == ld_ro(h.st_r + s1));
+        v = d_add(vit_ld(q, tab, PL_2, i, d - 1, s1, on2), wt);
+      }
+      w.part[a] = v;
+    }
+    double tsc2 = 0.;
+    bool c2P = gP;
+    if (gP && !ne) { tsc2 = e_sum_ext_m(m.en, q, i, j - 1, false) + m.en.mlintern; c2P = tsc2 > NINF; }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) {
+      double x = vit_seg_max(w.part, h.right_off, s);
+      if (c2P) {
+        int slot; const double lam = lam_of(m, s, slot);
+        x = vmax(x, d_add(tab[band_idx(q, PL_P, i, d, s)], d_mul(lam, tsc2)));
+      }
+      tab[band_idx(q, PL_2, i, d, s)] = x;
+      tab[band_idx(q, PL_1, i, d, s)] = vmax(d_add(x, 0.), d_add(w.curB[s], 0.));
+    }
+    w_sync();
+  }
+  // ---- M(i,j,s) <- M(i+1,j,s1) emitting x[i] | B(i,j,s)     (enum_M)
+  if (gM) {
+    const bool okM = ok_M(q, i + 1, d - 1);
+    const int on1 = vit_only(rg, i + 1, d - 1);
+    for (int a = lane; a < h.n_left; a += WARP_N) {
+      const int s = ld_ro(h.left_tgt + a), s1 = ld_ro(h.left_idx + a);
+      double v = NINF;
+      Emit em{3, i, -1, j, s, s1};
+      if (okM && con.ok(m, q, em)) {
+        const int sl = ld_ro(h.st_l + s), s1l = ld_ro(h.st_l + s1);
+        const double wt = single_wt(q, s1l, i, ld_ro(h.node + sl) == '.' && sl == s1l);
+        v = d_add(vit_ld(q, tab, PL_M, i + 1, d - 1, s1, on1), wt);
+      }
+      w.part[a] = v;
+    }
+    w_sync();
+    for (int s = lane; s < S; s += WARP_N) {
+      double x = vit_seg_max(w.part, h.left_off, s);
+      if (gB) x = vmax(x, d_add(w.curB[s], 0.));
+      tab[band_idx(q, PL_M, i, d, s)] = x;
+    }
+    w_sync();
+  }
+  // ---- E(i,j,s) <- M(i,j,s) | L(i,j,s) hairpin | P(k,l,s1) L(i,k,s2) L(l,j,s3)     (enum_E)
+  if (gE) {
+    for (int a = lane; a < h.n_quad; a += WARP_N) w.part[a] = NINF;
+    w_sync();
+    if (h.n_quad > 0) {
+      const int C = q.C, lo = d - C > 0 ? d - C : 0;
+      int n = 0;
+      auto flush = [&](int cnt) {
+        // loop energies one inner pair per lane, then every quad entry over the buffered pairs
+        w_sync();
+        for (int z = lane; z < cnt; z += WARP_N) w.bt[z] = ne ? 0. : e_loop(m.en, q, i - 1, j, w.bi[z], w.bj[z] - 1);
+        w_sync();
+        for (int a = lane; a < h.n_quad; a += WARP_N) {
+          const int s = ld_ro(h.quad_tgt + a), s1 = ld_ro(h.quad_s1 + a), s2 = ld_ro(h.quad_s2 + a), s3 = ld_ro(h.quad_s3 + a);
+          int slot; const double lam = lam_of(m, s, slot);
+          double v = w.part[a];
+          for (int pp = 0; pp < cnt; ++pp) {
+            const double tsc = w.bt[pp];
+            if (!(tsc > NINF)) continue;
+            const int k = w.bi[pp], l = w.bj[pp];
+            const int oP = vit_only(rg, k, l - k), oL = vit_only(rg, i, k - i), oR = vit_only(rg, l, j - l);
+            v = vmax(v, d_add(vit_ld(q, tab, PL_P, k, l - k, s1, oP),
+                              d_add(vit_ld(q, tab, PL_L, i, k - i, s2, oL),
+                                    d_add(vit_ld(q, tab, PL_L, l, j - l, s3, oR), d_mul(lam, tsc)))));
+          }
+          w.part[a] = v;
+        }
+        w_sync();
+      };
+      for (int u10 = 0; u10 <= C; u10 += WARP_N) {
+        const int u1 = u10 + lane, k = i + u1;
+        unsigned mk = 0u;
+        if (u1 <= C && d - u1 >= lo) {
+          mk = mask_window(q.bp + k * q.mw, q.mw, lo, d - u1 - lo + 1);
+          if (u1 == 0) mk &= ~(1u << (d - lo));
+        }
+        while (w_any(mk != 0u)) {
+          if (n > RELEM_VIT_CAP - WARP_N) { flush(n); n = 0; }
+          const bool has = mk != 0u;
+          int b = 0;
+          if (has) { b = bit_ffs(mk) - 1; mk &= mk - 1; }
+          const unsigned bal = w_ballot(has);
+          if (has) { const int pos = n + w_popc(bal & lanemask_lt()); w.bi[pos] = k; w.bj[pos] = k + lo + b; }
+          n += w_popc(bal);
+        }
+      }
+      if (n) flush(n);
+    }
+    double tM = 0., tH = 0.;
+    bool cM = gM, cH = true;
+    if (!ne) {
+      if (gM) { tM = e_sum_ext_m(m.en, q, j, i - 1, false) + (m.en.mlclosing + m.en.mlintern); cM = tM > NINF; }
+      tH = e_hairpin(m.en, q, i - 1, j);
+      cH = tH > NINF;
+    }
+    for (int s = lane; s < S; s += WARP_N) {
+      int slot; const double lam = lam_of(m, s, slot);
+      double x = vit_seg_max(w.part, h.quad_off, s);
+      if (cM) x = vmax(x, d_add(tab[band_idx(q, PL_M, i, d, s)], d_mul(lam, tM)));
+      if (cH && ld_ro(h.is_loop + s)) x = vmax(x, d_add(tab[band_idx(q, PL_L, i, d, s)], d_mul(lam, tH)));
+      tab[band_idx(q, PL_E, i, d, s)] = x;
+    }
+    w_sync();
+  }
+}
+
+// forward pass of one sequence by one CTA; one barrier per diagonal.  Units of a diagonal (a pack of WARP_N single-state
+// cells, or one full cell) are handed to the warps through a shared counter, the long packs first.
 template <class CON>
 RDEV void cta_viterbi_forward(const ModelView& m, const SeqView& q, double* tab, double* otab, const CON& con,
-                              const VitRegion& rg) {
+                              const VitRegion& rg, VitWarp& w, int* ctr) {
   const int S = q.S, L = q.L, W = q.W;
-  const int lane = lane_id(), w0 = warp_id(), nw = n_warps();
+  const int lane = lane_id();
+  VitRegion off = rg;
+  off.on = false;   // a single-state cell reads single-state entries only: no pruning test needed on its reads
+  for (int d = CTA_TID; d <= W; d += CTA_NTH) ctr[d] = 0;
+  CTA_SYNC();
   for (int d = 0; d <= W; ++d) {
     const int ncell = L + 1 - d;
     int nb, na;
     rg.cells(d, ncell, nb, na);
     const int nbg = nb + na, npack = (nbg + WARP_N - 1) / WARP_N, nfull = ncell - nbg;
-    // heavy units (full cells) first, the packs of single-state cells fill the tail
-    for (int u = w0; u < nfull + npack; u += nw) {
-      // one call site for both kinds of unit: (cell, first state, state stride, end)
-      int i, s0, s1, ds;
-      if (u < nfull) { i = nb + u; s0 = lane; s1 = S; ds = WARP_N; }
-      else {
-        const int t = (u - nfull) * WARP_N + lane;
-        const bool lead = t < nb;
-        i = lead ? t : ncell - na + (t - nb);
-        s0 = lead ? rg.s_bg0 : rg.s_bgM;
-        s1 = t < nbg ? s0 + 1 : s0;
-        ds = 1;
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = ctr_next(ctr + d);
+      u = w_shfl(u, 0);
+      if (u >= npack + nfull) break;
+      if (u < npack) {
+        const int t = u * WARP_N + lane;
+        if (t < nbg) {
+          const bool lead = t < nb;
+          vit_cell_state(m, q, tab, otab, con, off, lead ? t : ncell - na + (t - nb), d, lead ? rg.s_bg0 : rg.s_bgM);
+        }
+      } else {
+        vit_full_cell(m, q, tab, con, rg, nb + (u - npack), d, w);
       }
-      for (int s = s0; s < s1; s += ds) vit_cell_state(m, q, tab, otab, con, rg, i, d, s);
     }
     CTA_SYNC();
   }

@@ -260,20 +260,25 @@ static void apply_mode(relem_ctx* c) {
 
 // choose the number of resident CTAs (= scratch slots) and make sure the scratch fits
 int plan_launch(relem_ctx* c, const relem_batch* b, int nch, bool coupled, const void* kernel, Launch& L,
-                int max_n = 1 << 30) {
+                int max_n = 1 << 30, int threads = RELEM_CTA_THREADS) {
   int S = c->flat.S, M = c->flat.M;
   L.c = c;
-  L.lay = make_layout(std::max(1, b->Lmax), eff_span(c), S, M, c->n_theta, nch, coupled);
+  const FlatHMM& f = c->flat;
+  const size_t nlm = std::max(std::max(std::max(f.right_idx.size(), f.left_idx.size()), std::max(f.pair_idx.size(), f.split_left.size())),
+                              f.quad_s1.size());
+  L.lay = make_layout(std::max(1, b->Lmax), eff_span(c), S, M, c->n_theta, nch, coupled, (int)nlm);
+  const bool vit = threads == RELEM_VIT_THREADS;
+  const int sm_bytes = vit ? L.lay.sm_total_vit : L.lay.sm_total;
   unsigned long long band = (unsigned long long)NPLANE * (b->Lmax + 1) * (L.lay.Wmax + 1) * (coupled ? S : 1);
   if (band >= (1ull << 31)) return fail(c, RELEM_EINVAL, "band table of one sequence exceeds 2^31 entries");
 #ifdef RELEM_HOST_EMU
   (void)kernel;
   L.nslots = 1;
 #else
-  if (L.lay.sm_total > 227 * 1024) return fail(c, RELEM_EINVAL, "sequence too long: masks do not fit shared memory");
-  CUDA_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.lay.sm_total));
+  if (sm_bytes > 227 * 1024) return fail(c, RELEM_EINVAL, "sequence too long: masks do not fit shared memory");
+  CUDA_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
   int occ = 0;
-  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, RELEM_CTA_THREADS, L.lay.sm_total));
+  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, sm_bytes));
   if (occ < 1) return fail(c, RELEM_ECUDA, "kernel cannot be resident (occupancy 0)");
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
@@ -846,11 +851,13 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
 #ifndef RELEM_HOST_EMU
   CUDA_TRY(c, cudaSetDevice(c->dev));
 #endif
+  // slots (= resident CTAs) of the Viterbi kernel; the all-in-one log-space kernel plans its own further down, only
+  // when a sequence actually falls back to it
   Launch L;
 #ifdef RELEM_HOST_EMU
   rc = plan_launch(c, b, 1, true, nullptr, L);
 #else
-  rc = plan_launch(c, b, 1, true, (const void*)relem_scan_kernel, L);
+  rc = plan_launch(c, b, 1, true, (const void*)relem_viterbi_kernel, L, 1 << 30, RELEM_VIT_THREADS);
 #endif
   if (rc) return rc;
   size_t tl = (size_t)b->total_len;
@@ -885,7 +892,7 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
 #ifndef RELEM_HOST_EMU
     ll.stream = (void*)c->stream;
     CUDA_TRY(c, cudaFuncSetAttribute((const void*)relem_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     L.lay.sm_total));
+                                     L.lay.sm_total_vit));
 #else
     ll.stream = nullptr;
 #endif
@@ -903,7 +910,7 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
       relem_ctx* c = v.c;
 #ifdef RELEM_HOST_EMU
       *c->d_queue.as<int>() = 0;
-      std::vector<unsigned char> smem(v.L->lay.sm_total + 64);
+      std::vector<unsigned char> smem(std::max(v.L->lay.sm_total, v.L->lay.sm_total_vit) + 64);
       relem_viterbi_kernel(v.m, v.bv, v.L->lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), c->d_n2s.as<int>(), v.so,
                            em, c->d_flag.as<unsigned char>(), smem.data());
       return 0;
@@ -914,7 +921,7 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       v.ev.push_back(e0); v.ev.push_back(e1);
       cudaEventRecord(e0, st);
-      relem_viterbi_kernel<<<std::min(v.L->nslots, cv.count), RELEM_CTA_THREADS, v.L->lay.sm_total, st>>>(
+      relem_viterbi_kernel<<<std::min(v.L->nslots, cv.count), RELEM_VIT_THREADS, v.L->lay.sm_total_vit, st>>>(
           v.m, v.bv, v.L->lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), c->d_n2s.as<int>(), v.so, em,
           c->d_flag.as<unsigned char>());
       cudaEventRecord(e1, st);
@@ -954,6 +961,11 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
     }
   }
   if (n_fallback > 0) {
+#ifndef RELEM_HOST_EMU
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // the scratch may be re-allocated below
+    rc = plan_launch(c, b, 1, true, (const void*)relem_scan_kernel, L, n_fallback);
+    if (rc) return rc;
+#endif
     if (!Dev::zero(c->d_queue.p, sizeof(int))) return fail(c, RELEM_ECUDA, "queue reset failed");
     Timer t(c, "relem_scan_kernel");
 #ifdef RELEM_HOST_EMU

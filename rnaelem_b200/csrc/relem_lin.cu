@@ -31,6 +31,11 @@
 #include <cuda_runtime.h>
 #endif
 
+#ifdef RELEM_HOST_EMU
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
+#endif
+
 namespace relem {
 namespace lin {
 using namespace relem::dp;
@@ -254,7 +259,8 @@ LIN_KERNEL(LIN_THREADS, 8) relem_lin_prep_kernel(LinKArgs a LIN_SMEM_ARG) {
 // ------------------------------------------------------------------------------------------------ phases
 enum { PH_K0_IN = 0, PH_K0_OUT, PH_IN_L, PH_IN_P, PH_IN_B, PH_IN_E, PH_OUT_EM, PH_OUT_B, PH_OUT_P, PH_OUT_L,
        PH_OUT_LF, PH_OUT_LR,     // LF / LR: left / right flank gathers of outside L as kernels of their own
-       PH_OUT_PQ };              // enclosing interior loops of outside P
+       PH_OUT_PQ,                // enclosing interior loops of outside P
+       PH_OUT_ES };              // scatter mode: interior loops of E pushed down to P and the flanks (replaces PQ, LF, LR)
 
 // posterior sums of the CTA -> the sequence's accumulators in its slot header
 template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot, WarpLin& w, EhAcc<NCH>& eh) {
@@ -368,11 +374,51 @@ relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
       if (PH == PH_OUT_B) { if (ok_B(q, i, d)) lin_out_B<NCH, MODE>(c, t, i, d, ok_M(q, i, d), w); }
       if (PH == PH_OUT_P) { if (ok_P(q, i, d)) lin_out_P<NCH, MODE, 1>(c, t, i, d, ok_B(q, i, d), w, eh); }
       if (PH == PH_OUT_PQ) { if (ok_P(q, i, d)) lin_out_P<NCH, MODE, 2>(c, t, i, d, false, w, eh); }
+      if (PH == PH_OUT_ES) { if (ok_E(q, i, d)) lin_out_ES<NCH, MODE>(c, t, i, d, w, eh); }
       if (PH == PH_OUT_L) lin_out_L<NCH, MODE, 1>(c, t, i, d, d >= 3 && ok_E(q, i, d), w, eh);
       if (PH == PH_OUT_LF) lin_out_L<NCH, MODE, 2>(c, t, i, d, false, w, eh);
       if (PH == PH_OUT_LR) lin_out_L<NCH, MODE, 3>(c, t, i, d, false, w, eh);
     }
     if (PH != PH_OUT_LF && PH != PH_OUT_LR) lin_flush_counts<NCH>(lay, slot, w, eh);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ zero
+// scatter mode: b^P (every cell) and b^L (spans 1..Ceff, the possible flanks) start the outside pass at zero, because
+// lin_out_ES adds to them before their own phase runs.  128-bit stores over the contiguous b^P plane.
+template <int NCH> LIN_KERNEL(LIN_THREADS, 8) relem_lin_zero_kernel(LinKArgs a LIN_SMEM_ARG) {
+#ifdef RELEM_HOST_EMU
+  (void)smem_raw;
+#endif
+  const LinLayout& lay = a.lay;
+  const int blk = LIN_BLOCK_IDX;
+  const int sk = blk / a.ntile, tk = blk - sk * a.ntile;
+  if (sk >= a.count) return;
+  double* slot = a.scratch + (unsigned long long)sk * lay.stride;
+  if (slot[lay.hdr + 3] != 0.) return;
+  // the band tables of a slot are laid out with the sequence's OWN span W = min(L, max-span) (cidx), not the chunk's
+  const int L = (int)slot[lay.hdr + 5];
+  const int W = L < LC.en.max_span ? L : LC.en.max_span;
+  const int S = LC.h.S, W1 = W + 1;
+  const int C = W - 7 < LC.en.max_iloop ? W - 7 : LC.en.max_iloop;
+  const int Ceff = C < 30 ? C : 30;
+  // b^P: bch doubles per channel, even and 16-byte aligned (slot offsets are even, the scratch is 256-byte aligned)
+  const unsigned long long nP = (unsigned long long)NCH * lay.bch / 2;
+  double2* pP = reinterpret_cast<double2*>(slot + lay.bP);
+  for (unsigned long long z = (unsigned long long)tk * CTA_NTH + CTA_TID; z < nP; z += (unsigned long long)a.ntile * CTA_NTH)
+    pP[z] = make_double2(0., 0.);
+  if ((lay.bch & 1ull) && tk == 0 && CTA_TID == 0)
+    for (int ch = 0; ch < NCH; ++ch) slot[lay.bP + (unsigned long long)(ch + 1) * lay.bch - 1] = 0.;
+  if (Ceff >= 1) {
+    const unsigned per_row = (unsigned)Ceff * S;
+    const unsigned long long nL = (unsigned long long)(L + 1) * per_row;
+    for (int ch = 0; ch < NCH; ++ch) {
+      double* pL = slot + lay.bL + (unsigned long long)ch * lay.bch;
+      for (unsigned long long z = (unsigned long long)tk * CTA_NTH + CTA_TID; z < nL; z += (unsigned long long)a.ntile * CTA_NTH) {
+        unsigned row = (unsigned)(z / per_row), rem = (unsigned)(z - (unsigned long long)row * per_row);
+        pL[((unsigned long long)row * W1 + 1) * S + rem] = 0.;
+      }
+    }
   }
 }
 
@@ -784,6 +830,20 @@ template <int PH, int MODE> static void launch_phase3(Runner& r, int d, int tile
   r.mark(PH);
 }
 
+// scatter mode: zero b^P and the flank part of b^L of every slot of the chunk before its outside pass
+template <int NCH> static void launch_zero(Runner& r) {
+#if LIN_SCATTER_ILOOP
+  const unsigned long long per = (unsigned long long)NCH * r.a.lay.bch / 2;   // double2 stores per slot (the larger part)
+  long long nt = (long long)((per + 8ull * LIN_THREADS - 1) / (8ull * LIN_THREADS));   // ~8 stores per thread ...
+  const long long want = (long long)r.fill * r.resident_ctas;
+  if ((long long)r.a.count * nt > 4 * want) nt = std::max<long long>(1, 4 * want / r.a.count);   // ... but not more CTAs than the GPU chews
+  r.a.ntile = (int)nt; r.a.tile = 0; r.a.d = 0; r.a.win = 0;
+  LIN_LAUNCH(r, (relem_lin_zero_kernel<NCH>), r.a.count * r.a.ntile, LIN_THREADS, 0);
+#else
+  (void)r;
+#endif
+}
+
 template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
   const int W = r.a.lay.Wmax, cnt = r.a.count;
   LIN_LAUNCH(r, relem_lin_prep_kernel, cnt, LIN_THREADS, r.smem_small);
@@ -803,19 +863,27 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
     if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, r.tile_e, r.smem_in);
   }
   LIN_LAUNCH(r, (relem_lin_ext_kernel<2, NCH>), cnt, 32, r.smem_ext_in);
+  launch_zero<NCH>(r);
   LIN_LAUNCH(r, (relem_lin_ext_kernel<3, NCH>), cnt, 32, r.smem_ext_out);
   for (int d = W; d >= 0; --d) {
     if (d >= 3) launch_phase<PH_OUT_EM, NCH>(r, d, r.tile_p, r.smem_out);
+#if LIN_SCATTER_ILOOP
+    if (d >= 3) launch_phase<PH_OUT_ES, NCH>(r, d, r.tile_q, r.smem_out);
+#endif
     if (d >= 5) {
       launch_phase<PH_OUT_B, NCH>(r, d, r.tile_d, r.smem_out);
       launch_phase<PH_OUT_P, NCH>(r, d, r.tile_e, r.smem_out);
+#if !LIN_SCATTER_ILOOP
       launch_phase<PH_OUT_PQ, NCH>(r, d, r.tile_q, r.smem_out);
+#endif
     }
     launch_phase<PH_OUT_L, NCH>(r, d, r.tile_d, r.smem_out);
+#if !LIN_SCATTER_ILOOP
     if (d >= 1 && d <= r.cmax) {
       launch_phase<PH_OUT_LF, NCH>(r, d, r.tile_f, r.smem_out);
       launch_phase<PH_OUT_LR, NCH>(r, d, r.tile_f, r.smem_out);
     }
+#endif
   }
   LIN_LAUNCH(r, (relem_lin_fold_kernel<NCH>), cnt, LIN_THREADS, NCH * NT * 8 + 16);
 }
@@ -850,6 +918,7 @@ static void run_chunk_scan(Runner& r, bool filter, int NT) {
         if (d >= 3) launch_phase_win<PH_IN_E>(r, d, r.tile_e, r.smem_in);
       }
     }
+    launch_zero<1>(r);
     if (pass == 1) {
       LIN_LAUNCH(r, (relem_lin_ext_kernel<2, 1, 1>), cnt, 32, r.smem_ext_in);
       LIN_LAUNCH(r, (relem_lin_ext_kernel<3, 1, 1>), cnt, 32, r.smem_ext_out);
@@ -860,28 +929,42 @@ static void run_chunk_scan(Runner& r, bool filter, int NT) {
     for (int d = W; d >= 0; --d) {
       if (pass == 1) {
         if (d >= 3) launch_phase3<PH_OUT_EM, 1>(r, d, r.tile_p, r.smem_out);
+#if LIN_SCATTER_ILOOP
+        if (d >= 3) launch_phase3<PH_OUT_ES, 1>(r, d, r.tile_q, r.smem_out);
+#endif
         if (d >= 5) {
           launch_phase3<PH_OUT_B, 1>(r, d, r.tile_d, r.smem_out);
           launch_phase3<PH_OUT_P, 1>(r, d, r.tile_e, r.smem_out);
+#if !LIN_SCATTER_ILOOP
           launch_phase3<PH_OUT_PQ, 1>(r, d, r.tile_q, r.smem_out);
+#endif
         }
         launch_phase3<PH_OUT_L, 1>(r, d, r.tile_d, r.smem_out);
+#if !LIN_SCATTER_ILOOP
         if (d >= 1 && d <= r.cmax) {
           launch_phase3<PH_OUT_LF, 1>(r, d, r.tile_f, r.smem_out);
           launch_phase3<PH_OUT_LR, 1>(r, d, r.tile_f, r.smem_out);
         }
+#endif
       } else {
         if (d >= 3) launch_phase3<PH_OUT_EM, 2>(r, d, r.tile_p, r.smem_out);
+#if LIN_SCATTER_ILOOP
+        if (d >= 3) launch_phase3<PH_OUT_ES, 2>(r, d, r.tile_q, r.smem_out);
+#endif
         if (d >= 5) {
           launch_phase3<PH_OUT_B, 2>(r, d, r.tile_d, r.smem_out);
           launch_phase3<PH_OUT_P, 2>(r, d, r.tile_e, r.smem_out);
+#if !LIN_SCATTER_ILOOP
           launch_phase3<PH_OUT_PQ, 2>(r, d, r.tile_q, r.smem_out);
+#endif
         }
         launch_phase3<PH_OUT_L, 2>(r, d, r.tile_d, r.smem_out);
+#if !LIN_SCATTER_ILOOP
         if (d >= 1 && d <= r.cmax) {
           launch_phase3<PH_OUT_LF, 2>(r, d, r.tile_f, r.smem_out);
           launch_phase3<PH_OUT_LR, 2>(r, d, r.tile_f, r.smem_out);
         }
+#endif
       }
     }
     if (pass == 1) LIN_LAUNCH(r, (relem_lin_scanfold_kernel<1>), cnt, LIN_THREADS, NT * 8 + 16);
@@ -923,10 +1006,13 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   size_t per = (size_t)lay.stride * sizeof(double);
 #ifdef RELEM_HOST_EMU
   LC = hc;
-  if (per > st->scratch_bytes) {
+  // chunks of up to 4 sequences share one launch sequence, like a (tiny) device chunk: sequences of different length
+  // in one chunk exercise everything that depends on the chunk-wide layout versus the per-sequence one
+  const int emu_chunk = 4;
+  if (per * emu_chunk > st->scratch_bytes) {
     std::free(st->scratch);
-    st->scratch = std::malloc(per);
-    st->scratch_bytes = st->scratch ? per : 0;
+    st->scratch = std::malloc(per * emu_chunk);
+    st->scratch_bytes = st->scratch ? per * emu_chunk : 0;
   }
   if (!st->scratch) { err = "scratch allocation failed"; return 3; }
   std::free(st->k0pow);
@@ -935,10 +1021,10 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
   r.smem.assign(std::max(std::max(r.smem_out, r.smem_in), NT * in.nch * 8 + 16) + 64, 0);
   LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
-  for (int k = 0; k < nseq; ++k) {
+  for (int k = 0; k < nseq; k += emu_chunk) {
     // poison: the gather passes must never read an entry they did not write
-    { double* p = (double*)st->scratch; for (size_t z = 0; z < per / 8; ++z) p[z] = std::nan(""); }
-    a.base = k; a.count = 1;
+    { double* p = (double*)st->scratch; for (size_t z = 0; z < per * emu_chunk / 8; ++z) p[z] = std::nan(""); }
+    a.base = k; a.count = std::min(emu_chunk, nseq - k);
     if (in.nch == 2) run_chunk<2>(r, in.en.filter != 0, NT);
     else run_chunk<1>(r, in.en.filter != 0, NT);
   }
@@ -1048,7 +1134,8 @@ int lin_phase_timing(const LinState* st, const char** names, float* ms, int* lau
       "relem_lin_phase_kernel<6> outside E,M", "relem_lin_phase_kernel<7> outside 1,B,2",
       "relem_lin_phase_kernel<8> outside P (2<-P, stack, exterior)", "relem_lin_phase_kernel<9> outside L (hairpin, parent)",
       "relem_lin_phase_kernel<10> outside L left flanks", "relem_lin_phase_kernel<11> outside L right flanks",
-      "relem_lin_phase_kernel<12> outside P enclosing interior loops", "", "", ""};
+      "relem_lin_phase_kernel<12> outside P enclosing interior loops",
+      "relem_lin_phase_kernel<13> outside E interior loops (scatter to P and flanks)", "", ""};
   int n = 0;
   if (!st) return 0;
   for (int k = 0; k < LIN_NPHASE_SLOTS && n < cap; ++k) {
@@ -1088,10 +1175,11 @@ int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_ch
   cv.stride = lay.stride; cv.masks_off = lay.masks; cv.mask_words = lay.mask_words;
 #ifdef RELEM_HOST_EMU
   LC = hc;
-  if (per > st->scratch_bytes) {
+  const int emu_chunk = 4;   // see lin_estep_launch
+  if (per * emu_chunk > st->scratch_bytes) {
     std::free(st->scratch);
-    st->scratch = std::malloc(per);
-    st->scratch_bytes = st->scratch ? per : 0;
+    st->scratch = std::malloc(per * emu_chunk);
+    st->scratch_bytes = st->scratch ? per * emu_chunk : 0;
   }
   if (!st->scratch) { err = "scratch allocation failed"; return 3; }
   std::free(st->k0pow);
@@ -1100,11 +1188,11 @@ int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_ch
   a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
   r.smem.assign(std::max(std::max(r.smem_out, r.smem_in), NT * 8 + 16) + 64, 0);
   LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
-  for (int k = 0; k < nseq; ++k) {
-    { double* p = (double*)st->scratch; for (size_t z = 0; z < per / 8; ++z) p[z] = std::nan(""); }
-    a.base = k; a.count = 1;
+  for (int k = 0; k < nseq; k += emu_chunk) {
+    { double* p = (double*)st->scratch; for (size_t z = 0; z < per * emu_chunk / 8; ++z) p[z] = std::nan(""); }
+    a.base = k; a.count = std::min(emu_chunk, nseq - k);
     run_chunk_scan(r, in.en.filter != 0, NT);
-    cv.base = k; cv.count = 1; cv.scratch = a.scratch; cv.stream = nullptr;
+    cv.base = k; cv.count = a.count; cv.scratch = a.scratch; cv.stream = nullptr;
     if (after_chunk && after_chunk(user, cv)) { err = "Viterbi launch failed"; return 2; }
   }
   if (launches) *launches = r.launches;
