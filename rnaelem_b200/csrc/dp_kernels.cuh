@@ -14,7 +14,9 @@ namespace relem {
 namespace dp {
 
 #define RELEM_CTA_THREADS 128
+#ifndef RELEM_VIT_THREADS
 #define RELEM_VIT_THREADS 256   // Viterbi kernel: 8 warps share one sequence
+#endif
 
 // per-slot scratch, offsets in doubles from the slot base
 struct SlotLayout {
@@ -594,7 +596,7 @@ RELEM_VIT_KERNEL relem_viterbi_kernel(ModelView m, BatchView b, SlotLayout lay, 
     rg.ys = se.ys; rg.ye = se.ye; rg.s_bg0 = h.s00; rg.s_bgM = s_bgM;
     rg.on = h.s00 >= 0 && s_bgM >= 0 && se.ys >= 0 && se.ye >= se.ys;
     VitWarp vw = vit_warp_carve(smem_raw + lay.sm_vit_warp + warp_id() * lay.vit_warp_bytes, S, lay.vit_n_max);
-    cta_viterbi_forward(m, q, tab, otab, se, rg, vw, (int*)(smem_raw + lay.sm_vit_ctr));
+    cta_viterbi_forward(m, q, tab, otab, se, rg, vw);
     if (CTA_TID == 0) {
       double a = h.s0M2 >= 0 ? otab[L * S + h.s0M2] : NINF;
       double c = h.s0M1 >= 0 ? otab[L * S + h.s0M1] : NINF;

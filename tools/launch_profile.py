@@ -22,13 +22,15 @@ for r in rows[1:]:
     d[r[im]] = float(r[iv].replace(",", ""))
 agg = collections.OrderedDict()
 for d in per.values():
-    a = agg.setdefault(d["kernel"], [0, 0.0, 0.0, 0.0, 0.0])
+    a = agg.setdefault(d["kernel"], [0, 0.0, 0.0, 0.0, 0.0, 0.0])
     a[0] += 1
     a[1] += d.get("gpu__time_duration.sum", 0.0)
     a[2] += d.get("dram__bytes_read.sum", 0.0)
     a[3] += d.get("dram__bytes_write.sum", 0.0)
     a[4] += d.get("smsp__inst_executed.sum", 0.0)
-tot = [sum(a[k] for a in agg.values()) for k in range(5)]
+    # fp64 arithmetic thread-instructions (fused multiply-adds, multiplies, adds), when the pass collected them
+    a[5] += sum(d.get("smsp__sass_thread_inst_executed_op_%s_pred_on.sum" % op, 0.0) for op in ("dfma", "dmul", "dadd"))
+tot = [sum(a[k] for a in agg.values()) for k in range(6)]
 with open(out_md, "w") as f:
     f.write("| kernel | launches | ms | share | DRAM read GB | DRAM write GB | G warp-instr |\n|---|---|---|---|---|---|---|\n")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -38,5 +40,6 @@ json.dump({"command": cmd, "ncu": "--metrics dram__bytes_read.sum,dram__bytes_wr
            "sequence_evaluations": nse, "dram_bytes_read": tot[2], "dram_bytes_write": tot[3],
            "dram_bytes_per_sequence_evaluation": (tot[2] + tot[3]) / nse,
            "warp_instructions_per_sequence_evaluation": tot[4] / nse, "launches": tot[0],
+           "dfma_per_sequence_evaluation": tot[5] / nse,
            "sum_kernel_ms_under_ncu": tot[1] / 1e6}, open(out_json, "w"), indent=1)
 print(open(out_md).read())
