@@ -286,6 +286,29 @@ template <class V> RDEV void enum_O(const ModelView& m, const SeqView& q, int j,
   int a0 = ld_ro(h.split_off + s), a1 = ld_ro(h.split_off + s + 1);
   int i0 = j - q.W > 0 ? j - q.W : 0;
   Emit em0{0, -1, -1, j, s, s};
+  if (a0 == a1) {
+    // a state without splits takes no pair: nothing to visit
+  } else if (q.bpr) {
+    // same visiting order (i descending = span ascending), pairs closed at j found by scanning row j of the
+    // right-indexed pair mask
+    const unsigned* rj = q.bpr + j * q.mw;
+    const int dmax = j - i0;
+    for (int lo = 0; lo <= dmax; lo += 32) {
+      unsigned mk = mask_window(rj, q.mw, lo, dmax - lo + 1 < 32 ? dmax - lo + 1 : 32);
+      while (mk) {
+        const int t = bit_ffs(mk) - 1;
+        mk &= mk - 1;
+        const int i = j - (lo + t);
+        double tsc = m.en.no_ene ? 0. : e_sum_ext_m(m.en, q, i, j - 1, true);
+        if (!(tsc > NINF)) continue;
+        double lt = d_mul(lam, tsc);
+        for (int a = a0; a < a1; ++a) {
+          int sl = ld_ro(h.split_left + a), sr = ld_ro(h.split_right + a);
+          v.o2(TT_O_OP, (unsigned)(i * q.S + sl), v.bidx(q, PL_P, i, j - i, sr), lt, tsc, slot, em0, Geo{i, j, sr});
+        }
+      }
+    }
+  } else
   for (int i = j; i >= i0; --i) {
     if (!ok_P(q, i, j - i)) continue;
     double tsc = m.en.no_ene ? 0. : e_sum_ext_m(m.en, q, i, j - 1, true);

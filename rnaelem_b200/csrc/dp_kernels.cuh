@@ -15,7 +15,9 @@ namespace dp {
 
 #define RELEM_CTA_THREADS 128
 #ifndef RELEM_VIT_THREADS
-#define RELEM_VIT_THREADS 256   // Viterbi kernel: 8 warps share one sequence
+#define RELEM_VIT_THREADS 64    // Viterbi kernel: 2 warps share one sequence.  Small CTAs on purpose: the exterior row and
+                                // the traceback of a sequence are serial, and with many independent CTAs per SM the
+                                // serial part of one overlaps the band sweep of the others (profiles/r2_viterbi.md)
 #endif
 
 // per-slot scratch, offsets in doubles from the slot base
@@ -546,7 +548,7 @@ struct ExtMasks {
 #ifdef RELEM_HOST_EMU
 #define RELEM_VIT_KERNEL inline void
 #else
-#define RELEM_VIT_KERNEL __global__ void __launch_bounds__(RELEM_VIT_THREADS, 2)
+#define RELEM_VIT_KERNEL __global__ void __launch_bounds__(RELEM_VIT_THREADS, 512 / RELEM_VIT_THREADS)
 #endif
 RELEM_VIT_KERNEL relem_viterbi_kernel(ModelView m, BatchView b, SlotLayout lay, double* scratch, int* queue, const int* n2s,
                                   ScanOut out, ExtMasks em, const unsigned char* flag RELEM_SMEM_ARG) {

@@ -235,17 +235,42 @@ struct K0Tabs {
   double *P, *E, *M, *o1, *o2, *O;
   double *bP, *bE, *bM, *bBl, *bBr, *b2, *bO;
   double* Pm;        // P(k,l) times the interior mismatch factor on the inner pair's side (by right end, like P)
+  double* Pn;        // ... times the 1xn mismatch factor (mismatch_1ni) on the inner pair's side
+  double* Pu;        // ... times the terminal-AU factor of the inner pair (bulges of length >= 2)
   double* bEm;       // outside E(i,j) times the interior mismatch factor on the closing pair's side
-  const double* G;   // [32][32] internal[u1+u2] * ninio[|u1-u2|] * kappa0^(u1+u2) for u1,u2 >= 3
+  double* bEn;       // ... times the 1xn mismatch factor on the closing pair's side
+  double* bEu;       // ... times the terminal-AU factor of the closing pair
+  const double* G;   // [32][32] length part of a separable loop times kappa0^(u1+u2): internal[u1+u2] * ninio[|u1-u2|]
+                     // for u1,u2 >= 1; bulge[u] in row / column 0 (u >= 2)
   double *eO, *fO;   // [L+1] power-of-two exponents of the exterior rows O / bO (stored as doubles)
 };
 
-// Interior loops of the energy-only pass.  For u1,u2 >= 3 the loop energy is separable (energy_param.hpp:781-794:
-// length term + asymmetry term + one mismatch term per closing pair, always from the generic mismatch table), so the
-// sum over inner pairs is  mm(outer) * sum_{k,l} [P(k,l) mm(inner)] * G[u1][u2]  with the bracket stored once per
-// pair: two loads and one FMA per candidate.  The remaining ("special": stack, bulges, 1x1, 1x2, 2x2, 1xn, 2x3) candidates
-// are compacted across the warp and evaluated by the full case analysis, one per lane.
+// Interior loops of the energy-only pass.  Most loop energies are separable (energy_param.hpp:744-794): a length term
+// times one factor per closing pair,
+//   class G  u1,u2 >= 2, u1+u2 >= 6          internal * ninio * mismatch_i(outer)   * mismatch_i(inner)
+//   class N  (1, n >= 3), (n >= 3, 1)        internal * ninio * mismatch_1ni(outer) * mismatch_1ni(inner)
+//   class U  bulges of length >= 2           bulge             * termAU(outer)       * termAU(inner)
+// so the sum over the inner pairs of a class is  f(outer) * sum_{k,l} [P(k,l) f(inner)] * G[u1][u2]  with the bracket
+// stored once per pair (planes Pm, Pn, Pu): two loads and one FMA per candidate.  The eight remaining shapes (bulge of 1,
+// 1x1, 1x2, 2x1, 2x2, 2x3, 3x2) are compacted across the warp and evaluated by the full case analysis, one per lane.
 // sbuf: per-warp scratch of 128 ints.
+//
+// class masks over u2 for a lane's u1 (bit t <-> u2 = t; callers reverse for windows indexed the other way):
+RDEV void k0_class_masks(int u1, unsigned& mG, unsigned& mN, unsigned& mU) {
+  // u2 >= 2 with u1+u2 >= 6 (u1 >= 2);  u2 == 1 (u1 >= 3) or u2 >= 3 (u1 == 1);  u2 == 0 (u1 >= 2) or u2 >= 2 (u1 == 0)
+  mG = 0u; mN = 0u; mU = 0u;
+  if (u1 == 0) mU = ~3u;
+  else if (u1 == 1) mN = ~7u;
+  else {
+    mU = 1u;
+    if (u1 >= 3) mN = 2u;
+    const int lo2 = 6 - u1 > 2 ? 6 - u1 : 2;   // smallest u2 of class G
+    mG = ~((1u << lo2) - 1u);
+  }
+}
+RDEV unsigned k0_rev_window(unsigned m, int top) {   // bit t of the result = bit (top - t) of m, top in 0..31
+  return bit_rev(m) >> (31 - top);
+}
 RDEV void k0_specials_push(int* sbuf, int& ns, unsigned sp, int u1) {
   // exclusive prefix of the per-lane counts, then every lane writes its own candidates
   int cnt = w_popc(sp), pre = cnt;
@@ -309,7 +334,7 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* sb
   if (gE) {
     const int C = c.Ceff;
     const int lo = d - C > 0 ? d - C : 0;
-    double acc = 0., accg = 0.;
+    double acc = 0., accg = 0., accn = 0., accu = 0.;
     for (int u10 = 0; u10 <= C; u10 += WARP_N) {
       int u1 = u10 + lane, k = i + u1;
       unsigned m = 0u;
@@ -317,18 +342,24 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* sb
         m = win_bits(q.bp + k * q.mw, q.mw, lo, d - u1 - lo + 1);
         if (u1 == 0) m &= ~(1u << (d - lo));
       }
-      // generic candidates: u1 >= 3 and u2 = d-u1-dd >= 3  <=>  bit index b = dd-lo <= d-u1-3-lo
-      unsigned gen = 0u;
-      if (!ne && u1 >= 3) {
-        int top = d - u1 - 3 - lo;
-        if (top >= 0) gen = m & (top >= 31 ? 0xFFFFFFFFu : ((2u << top) - 1u));
+      // separable candidates by class: bit b <-> dd = lo + b <-> u2 = (d - u1 - lo) - b
+      unsigned gG = 0u, gN = 0u, gU = 0u;
+      const int top = d - u1 - lo;
+      if (!ne && m) {
+        unsigned cG, cN, cU;
+        k0_class_masks(u1, cG, cN, cU);
+        const unsigned mr = k0_rev_window(m, top);   // indexed by u2
+        gG = mr & cG; gN = mr & cN; gU = mr & cU;
       }
-      unsigned sp = m & ~gen;
-      while (gen) {
-        int b = w_ffs(gen) - 1;
+      unsigned sp = (gG | gN | gU) ? (m & ~k0_rev_window(gG | gN | gU, top)) : m;
+      for (unsigned gen = gG | gN | gU; gen;) {
+        const int u2 = w_ffs(gen) - 1;
         gen &= gen - 1;
-        int dd = lo + b, l = k + dd, u2 = d - u1 - dd;
-        accg += t.Pm[kidx(q, l, dd)] * ld_ro(t.G + u1 * 32 + u2);
+        const int dd = d - u1 - u2, l = k + dd;
+        const unsigned bit = 1u << u2;
+        const double* pl = (gG & bit) ? t.Pm : (gN & bit) ? t.Pn : t.Pu;
+        const double v = pl[kidx(q, l, dd)] * ld_ro(t.G + u1 * 32 + u2);
+        if (gG & bit) accg += v; else if (gN & bit) accn += v; else accu += v;
       }
       int ns = 0;
       k0_specials_push(sbuf, ns, sp, u1);
@@ -342,10 +373,11 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* sb
       w_sync();
     }
     if (!ne) {
-      int type = bp_type(q.x[i - 1], q.x[j]);
-      accg *= ld_ro(el.mismatch_i + (type * 5 + q.x[i]) * 5 + q.x[j - 1]);
+      // the closing pair's factors are the same for every lane: fold the classes before the one warp reduction
+      const int type = bp_type(q.x[i - 1], q.x[j]);
+      const int mi = (type * 5 + q.x[i]) * 5 + q.x[j - 1];
+      acc += accg * ld_ro(el.mismatch_i + mi) + accn * ld_ro(el.mismatch_1ni + mi) + accu * (type > 2 ? el.term_au : 1.);
     }
-    acc += accg;
     vE = w_sum(acc);
     if (gM) vE += vM * (ne ? 1. : nl_l_ext(&q, j, i - 1, 0) * (el.mlclosing * el.mlintern));
     if (d >= 1) vE += c.k0pow[d] * (ne ? 1. : nl_l_hairpin(&q, i - 1, j));
@@ -353,10 +385,17 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* sb
   if (lane == 0) {
     if (gP) {
       t.P[kidx(q, j, d)] = vP;
-      // inner-pair side mismatch of a generic interior loop: pair (i, j-1), neighbours x[j] and x[i-1]
-      double mmf = 0.;
-      if (i >= 1 && j < q.L) mmf = ld_ro(el.mismatch_i + (bp_type(q.x[j - 1], q.x[i]) * 5 + q.x[j]) * 5 + q.x[i - 1]);
+      // inner-pair side factors of the separable loop classes: pair (i, j-1), neighbours x[j] and x[i-1]
+      double mmf = 0., mnf = 0.;
+      const int ty = bp_type(q.x[j - 1], q.x[i]);
+      if (i >= 1 && j < q.L) {
+        const int mi = (ty * 5 + q.x[j]) * 5 + q.x[i - 1];
+        mmf = ld_ro(el.mismatch_i + mi);
+        mnf = ld_ro(el.mismatch_1ni + mi);
+      }
       t.Pm[kidx(q, j, d)] = vP * mmf;
+      t.Pn[kidx(q, j, d)] = vP * mnf;
+      t.Pu[kidx(q, j, d)] = vP * (ty > 2 ? el.term_au : 1.);
     }
     if (gB) { t.o1[kidx(q, i, d)] = v1; t.o2[kidx(q, j, d)] = v2; }
     if (gM) t.M[kidx(q, i, d)] = vM;
@@ -468,7 +507,7 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* s
     // enclosing pairs: this cell is the inner pair (k=i,l=j) of E(i',j')
     const int C = c.Ceff;
     const int hi = W < d + C + 2 ? W : d + C + 2;
-    double acc = 0., accg = 0.;
+    double acc = 0., accg = 0., accn = 0., accu = 0.;
     for (int u10 = 0; u10 <= C; u10 += WARP_N) {
       int u1 = u10 + lane, i2 = i - u1, lo = d + u1 + 2;
       unsigned m = 0u;
@@ -476,12 +515,20 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* s
         m = win_bits(q.bp + (i2 - 1) * q.mw, q.mw, lo, hi - lo + 1);
         if (u1 == 0) m &= ~1u;
       }
-      unsigned gen = (!ne && u1 >= 3) ? (m & ~7u) : 0u;   // bit index = u2
-      unsigned sp = m & ~gen;
-      while (gen) {
-        int u2 = w_ffs(gen) - 1;
+      unsigned gG = 0u, gN = 0u, gU = 0u;   // bit index = u2
+      if (!ne && m) {
+        unsigned cG, cN, cU;
+        k0_class_masks(u1, cG, cN, cU);
+        gG = m & cG; gN = m & cN; gU = m & cU;
+      }
+      unsigned sp = m & ~(gG | gN | gU);
+      for (unsigned gen = gG | gN | gU; gen;) {
+        const int u2 = w_ffs(gen) - 1;
         gen &= gen - 1;
-        accg += t.bEm[kidx(q, i2, d + u1 + u2)] * ld_ro(t.G + u1 * 32 + u2);
+        const unsigned bit = 1u << u2;
+        const double* pl = (gG & bit) ? t.bEm : (gN & bit) ? t.bEn : t.bEu;
+        const double v = pl[kidx(q, i2, d + u1 + u2)] * ld_ro(t.G + u1 * 32 + u2);
+        if (gG & bit) accg += v; else if (gN & bit) accn += v; else accu += v;
       }
       int ns = 0;
       k0_specials_push(sbuf, ns, sp, u1);
@@ -494,18 +541,27 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* s
       }
       w_sync();
     }
-    if (!ne && i >= 1 && j < L)
-      accg *= ld_ro(el.mismatch_i + (bp_type(q.x[j - 1], q.x[i]) * 5 + q.x[j]) * 5 + q.x[i - 1]);
-    else accg = 0.;
-    acc += accg;
+    if (!ne) {
+      // this (inner) pair's factors are the same for every lane; a pair at the sequence boundary has no mismatch
+      const int ty = bp_type(q.x[j - 1], q.x[i]);
+      if (i >= 1 && j < L) {
+        const int mi = (ty * 5 + q.x[j]) * 5 + q.x[i - 1];
+        acc += accg * ld_ro(el.mismatch_i + mi) + accn * ld_ro(el.mismatch_1ni + mi);
+      }
+      acc += accu * (ty > 2 ? el.term_au : 1.);
+    }
     bP += w_sum(acc);
   }
   if (lane == 0) {
     if (gP) t.bP[kidx(q, i, d)] = bP;
     if (gE) {
       t.bE[kidx(q, i, d)] = bE;
-      // closing-pair side mismatch of a generic interior loop: pair (i-1, j), neighbours x[i] and x[j-1]
-      t.bEm[kidx(q, i, d)] = bE * ld_ro(el.mismatch_i + (bp_type(q.x[i - 1], q.x[j]) * 5 + q.x[i]) * 5 + q.x[j - 1]);
+      // closing-pair side factors of the separable loop classes: pair (i-1, j), neighbours x[i] and x[j-1]
+      const int ty = bp_type(q.x[i - 1], q.x[j]);
+      const int mi = (ty * 5 + q.x[i]) * 5 + q.x[j - 1];
+      t.bEm[kidx(q, i, d)] = bE * ld_ro(el.mismatch_i + mi);
+      t.bEn[kidx(q, i, d)] = bE * ld_ro(el.mismatch_1ni + mi);
+      t.bEu[kidx(q, i, d)] = bE * (ty > 2 ? el.term_au : 1.);
     }
     if (gM) t.bM[kidx(q, i, d)] = bM;
     if (gB) { t.bBl[kidx(q, i, d)] = bB; t.bBr[kidx(q, j, d)] = bB; t.b2[kidx(q, i, d)] = b2; }
