@@ -15,9 +15,7 @@ namespace dp {
 
 #define RELEM_CTA_THREADS 128
 #ifndef RELEM_VIT_THREADS
-#define RELEM_VIT_THREADS 64    // Viterbi kernel: 2 warps share one sequence.  Small CTAs on purpose: the exterior row and
-                                // the traceback of a sequence are serial, and with many independent CTAs per SM the
-                                // serial part of one overlaps the band sweep of the others (profiles/r2_viterbi.md)
+#define RELEM_VIT_THREADS 256   // Viterbi kernel: 8 warps share one sequence (measured against 64: profiles/r2_viterbi.md)
 #endif
 
 // per-slot scratch, offsets in doubles from the slot base

@@ -61,6 +61,18 @@ using namespace relem::dp;
 #define LIN_SCATTER_ILOOP 1
 #endif
 
+// Split gathers through shared memory with the bulk-copy engine (TMA, cp.async.bulk + mbarrier), A/B switch.
+// 1: the [cell][state] vectors of up to LIN_TMA_STAGES split points are fetched by one 1-D bulk copy each into a
+// per-warp staging buffer (no registers, no scoreboard: the whole batch is in flight at once), the lanes then take
+// their operands from shared memory.  Needs 16-byte aligned vectors, i.e. an even number of states; other automata use
+// the direct gathers.  0: direct per-lane gathers with four split points in flight.  Measured: profiles/r2_tma_ab.md.
+#ifndef LIN_SPLIT_TMA
+#define LIN_SPLIT_TMA 0
+#endif
+#ifndef LIN_TMA_STAGES
+#define LIN_TMA_STAGES 16
+#endif
+
 struct LinEnergyScalars {  // linear-domain copies of the scalar energy terms
   double term_au, mlintern, mlclosing;
 };
@@ -235,42 +247,17 @@ struct K0Tabs {
   double *P, *E, *M, *o1, *o2, *O;
   double *bP, *bE, *bM, *bBl, *bBr, *b2, *bO;
   double* Pm;        // P(k,l) times the interior mismatch factor on the inner pair's side (by right end, like P)
-  double* Pn;        // ... times the 1xn mismatch factor (mismatch_1ni) on the inner pair's side
-  double* Pu;        // ... times the terminal-AU factor of the inner pair (bulges of length >= 2)
   double* bEm;       // outside E(i,j) times the interior mismatch factor on the closing pair's side
-  double* bEn;       // ... times the 1xn mismatch factor on the closing pair's side
-  double* bEu;       // ... times the terminal-AU factor of the closing pair
-  const double* G;   // [32][32] length part of a separable loop times kappa0^(u1+u2): internal[u1+u2] * ninio[|u1-u2|]
-                     // for u1,u2 >= 1; bulge[u] in row / column 0 (u >= 2)
+  const double* G;   // [32][32] internal[u1+u2] * ninio[|u1-u2|] * kappa0^(u1+u2) for u1,u2 >= 3
   double *eO, *fO;   // [L+1] power-of-two exponents of the exterior rows O / bO (stored as doubles)
 };
 
-// Interior loops of the energy-only pass.  Most loop energies are separable (energy_param.hpp:744-794): a length term
-// times one factor per closing pair,
-//   class G  u1,u2 >= 2, u1+u2 >= 6          internal * ninio * mismatch_i(outer)   * mismatch_i(inner)
-//   class N  (1, n >= 3), (n >= 3, 1)        internal * ninio * mismatch_1ni(outer) * mismatch_1ni(inner)
-//   class U  bulges of length >= 2           bulge             * termAU(outer)       * termAU(inner)
-// so the sum over the inner pairs of a class is  f(outer) * sum_{k,l} [P(k,l) f(inner)] * G[u1][u2]  with the bracket
-// stored once per pair (planes Pm, Pn, Pu): two loads and one FMA per candidate.  The eight remaining shapes (bulge of 1,
-// 1x1, 1x2, 2x1, 2x2, 2x3, 3x2) are compacted across the warp and evaluated by the full case analysis, one per lane.
+// Interior loops of the energy-only pass.  For u1,u2 >= 3 the loop energy is separable (energy_param.hpp:781-794:
+// length term + asymmetry term + one mismatch term per closing pair, always from the generic mismatch table), so the
+// sum over inner pairs is  mm(outer) * sum_{k,l} [P(k,l) mm(inner)] * G[u1][u2]  with the bracket stored once per
+// pair: two loads and one FMA per candidate.  The remaining ("special": stack, bulges, 1x1, 1x2, 2x2, 1xn, 2x3) candidates
+// are compacted across the warp and evaluated by the full case analysis, one per lane.
 // sbuf: per-warp scratch of 128 ints.
-//
-// class masks over u2 for a lane's u1 (bit t <-> u2 = t; callers reverse for windows indexed the other way):
-RDEV void k0_class_masks(int u1, unsigned& mG, unsigned& mN, unsigned& mU) {
-  // u2 >= 2 with u1+u2 >= 6 (u1 >= 2);  u2 == 1 (u1 >= 3) or u2 >= 3 (u1 == 1);  u2 == 0 (u1 >= 2) or u2 >= 2 (u1 == 0)
-  mG = 0u; mN = 0u; mU = 0u;
-  if (u1 == 0) mU = ~3u;
-  else if (u1 == 1) mN = ~7u;
-  else {
-    mU = 1u;
-    if (u1 >= 3) mN = 2u;
-    const int lo2 = 6 - u1 > 2 ? 6 - u1 : 2;   // smallest u2 of class G
-    mG = ~((1u << lo2) - 1u);
-  }
-}
-RDEV unsigned k0_rev_window(unsigned m, int top) {   // bit t of the result = bit (top - t) of m, top in 0..31
-  return bit_rev(m) >> (31 - top);
-}
 RDEV void k0_specials_push(int* sbuf, int& ns, unsigned sp, int u1) {
   // exclusive prefix of the per-lane counts, then every lane writes its own candidates
   int cnt = w_popc(sp), pre = cnt;
@@ -334,7 +321,7 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* sb
   if (gE) {
     const int C = c.Ceff;
     const int lo = d - C > 0 ? d - C : 0;
-    double acc = 0., accg = 0., accn = 0., accu = 0.;
+    double acc = 0., accg = 0.;
     for (int u10 = 0; u10 <= C; u10 += WARP_N) {
       int u1 = u10 + lane, k = i + u1;
       unsigned m = 0u;
@@ -342,24 +329,18 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* sb
         m = win_bits(q.bp + k * q.mw, q.mw, lo, d - u1 - lo + 1);
         if (u1 == 0) m &= ~(1u << (d - lo));
       }
-      // separable candidates by class: bit b <-> dd = lo + b <-> u2 = (d - u1 - lo) - b
-      unsigned gG = 0u, gN = 0u, gU = 0u;
-      const int top = d - u1 - lo;
-      if (!ne && m) {
-        unsigned cG, cN, cU;
-        k0_class_masks(u1, cG, cN, cU);
-        const unsigned mr = k0_rev_window(m, top);   // indexed by u2
-        gG = mr & cG; gN = mr & cN; gU = mr & cU;
+      // generic candidates: u1 >= 3 and u2 = d-u1-dd >= 3  <=>  bit index b = dd-lo <= d-u1-3-lo
+      unsigned gen = 0u;
+      if (!ne && u1 >= 3) {
+        int top = d - u1 - 3 - lo;
+        if (top >= 0) gen = m & (top >= 31 ? 0xFFFFFFFFu : ((2u << top) - 1u));
       }
-      unsigned sp = (gG | gN | gU) ? (m & ~k0_rev_window(gG | gN | gU, top)) : m;
-      for (unsigned gen = gG | gN | gU; gen;) {
-        const int u2 = w_ffs(gen) - 1;
+      unsigned sp = m & ~gen;
+      while (gen) {
+        int b = w_ffs(gen) - 1;
         gen &= gen - 1;
-        const int dd = d - u1 - u2, l = k + dd;
-        const unsigned bit = 1u << u2;
-        const double* pl = (gG & bit) ? t.Pm : (gN & bit) ? t.Pn : t.Pu;
-        const double v = pl[kidx(q, l, dd)] * ld_ro(t.G + u1 * 32 + u2);
-        if (gG & bit) accg += v; else if (gN & bit) accn += v; else accu += v;
+        int dd = lo + b, l = k + dd, u2 = d - u1 - dd;
+        accg += t.Pm[kidx(q, l, dd)] * ld_ro(t.G + u1 * 32 + u2);
       }
       int ns = 0;
       k0_specials_push(sbuf, ns, sp, u1);
@@ -373,11 +354,10 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* sb
       w_sync();
     }
     if (!ne) {
-      // the closing pair's factors are the same for every lane: fold the classes before the one warp reduction
-      const int type = bp_type(q.x[i - 1], q.x[j]);
-      const int mi = (type * 5 + q.x[i]) * 5 + q.x[j - 1];
-      acc += accg * ld_ro(el.mismatch_i + mi) + accn * ld_ro(el.mismatch_1ni + mi) + accu * (type > 2 ? el.term_au : 1.);
+      int type = bp_type(q.x[i - 1], q.x[j]);
+      accg *= ld_ro(el.mismatch_i + (type * 5 + q.x[i]) * 5 + q.x[j - 1]);
     }
+    acc += accg;
     vE = w_sum(acc);
     if (gM) vE += vM * (ne ? 1. : nl_l_ext(&q, j, i - 1, 0) * (el.mlclosing * el.mlintern));
     if (d >= 1) vE += c.k0pow[d] * (ne ? 1. : nl_l_hairpin(&q, i - 1, j));
@@ -385,17 +365,10 @@ RDEV void k0_inside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* sb
   if (lane == 0) {
     if (gP) {
       t.P[kidx(q, j, d)] = vP;
-      // inner-pair side factors of the separable loop classes: pair (i, j-1), neighbours x[j] and x[i-1]
-      double mmf = 0., mnf = 0.;
-      const int ty = bp_type(q.x[j - 1], q.x[i]);
-      if (i >= 1 && j < q.L) {
-        const int mi = (ty * 5 + q.x[j]) * 5 + q.x[i - 1];
-        mmf = ld_ro(el.mismatch_i + mi);
-        mnf = ld_ro(el.mismatch_1ni + mi);
-      }
+      // inner-pair side mismatch of a generic interior loop: pair (i, j-1), neighbours x[j] and x[i-1]
+      double mmf = 0.;
+      if (i >= 1 && j < q.L) mmf = ld_ro(el.mismatch_i + (bp_type(q.x[j - 1], q.x[i]) * 5 + q.x[j]) * 5 + q.x[i - 1]);
       t.Pm[kidx(q, j, d)] = vP * mmf;
-      t.Pn[kidx(q, j, d)] = vP * mnf;
-      t.Pu[kidx(q, j, d)] = vP * (ty > 2 ? el.term_au : 1.);
     }
     if (gB) { t.o1[kidx(q, i, d)] = v1; t.o2[kidx(q, j, d)] = v2; }
     if (gM) t.M[kidx(q, i, d)] = vM;
@@ -507,7 +480,7 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* s
     // enclosing pairs: this cell is the inner pair (k=i,l=j) of E(i',j')
     const int C = c.Ceff;
     const int hi = W < d + C + 2 ? W : d + C + 2;
-    double acc = 0., accg = 0., accn = 0., accu = 0.;
+    double acc = 0., accg = 0.;
     for (int u10 = 0; u10 <= C; u10 += WARP_N) {
       int u1 = u10 + lane, i2 = i - u1, lo = d + u1 + 2;
       unsigned m = 0u;
@@ -515,20 +488,12 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* s
         m = win_bits(q.bp + (i2 - 1) * q.mw, q.mw, lo, hi - lo + 1);
         if (u1 == 0) m &= ~1u;
       }
-      unsigned gG = 0u, gN = 0u, gU = 0u;   // bit index = u2
-      if (!ne && m) {
-        unsigned cG, cN, cU;
-        k0_class_masks(u1, cG, cN, cU);
-        gG = m & cG; gN = m & cN; gU = m & cU;
-      }
-      unsigned sp = m & ~(gG | gN | gU);
-      for (unsigned gen = gG | gN | gU; gen;) {
-        const int u2 = w_ffs(gen) - 1;
+      unsigned gen = (!ne && u1 >= 3) ? (m & ~7u) : 0u;   // bit index = u2
+      unsigned sp = m & ~gen;
+      while (gen) {
+        int u2 = w_ffs(gen) - 1;
         gen &= gen - 1;
-        const unsigned bit = 1u << u2;
-        const double* pl = (gG & bit) ? t.bEm : (gN & bit) ? t.bEn : t.bEu;
-        const double v = pl[kidx(q, i2, d + u1 + u2)] * ld_ro(t.G + u1 * 32 + u2);
-        if (gG & bit) accg += v; else if (gN & bit) accn += v; else accu += v;
+        accg += t.bEm[kidx(q, i2, d + u1 + u2)] * ld_ro(t.G + u1 * 32 + u2);
       }
       int ns = 0;
       k0_specials_push(sbuf, ns, sp, u1);
@@ -541,32 +506,52 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* s
       }
       w_sync();
     }
-    if (!ne) {
-      // this (inner) pair's factors are the same for every lane; a pair at the sequence boundary has no mismatch
-      const int ty = bp_type(q.x[j - 1], q.x[i]);
-      if (i >= 1 && j < L) {
-        const int mi = (ty * 5 + q.x[j]) * 5 + q.x[i - 1];
-        acc += accg * ld_ro(el.mismatch_i + mi) + accn * ld_ro(el.mismatch_1ni + mi);
-      }
-      acc += accu * (ty > 2 ? el.term_au : 1.);
-    }
+    if (!ne && i >= 1 && j < L)
+      accg *= ld_ro(el.mismatch_i + (bp_type(q.x[j - 1], q.x[i]) * 5 + q.x[j]) * 5 + q.x[i - 1]);
+    else accg = 0.;
+    acc += accg;
     bP += w_sum(acc);
   }
   if (lane == 0) {
     if (gP) t.bP[kidx(q, i, d)] = bP;
     if (gE) {
       t.bE[kidx(q, i, d)] = bE;
-      // closing-pair side factors of the separable loop classes: pair (i-1, j), neighbours x[i] and x[j-1]
-      const int ty = bp_type(q.x[i - 1], q.x[j]);
-      const int mi = (ty * 5 + q.x[i]) * 5 + q.x[j - 1];
-      t.bEm[kidx(q, i, d)] = bE * ld_ro(el.mismatch_i + mi);
-      t.bEn[kidx(q, i, d)] = bE * ld_ro(el.mismatch_1ni + mi);
-      t.bEu[kidx(q, i, d)] = bE * (ty > 2 ? el.term_au : 1.);
+      // closing-pair side mismatch of a generic interior loop: pair (i-1, j), neighbours x[i] and x[j-1]
+      t.bEm[kidx(q, i, d)] = bE * ld_ro(el.mismatch_i + (bp_type(q.x[i - 1], q.x[j]) * 5 + q.x[i]) * 5 + q.x[j - 1]);
     }
     if (gM) t.bM[kidx(q, i, d)] = bM;
     if (gB) { t.bBl[kidx(q, i, d)] = bB; t.bBr[kidx(q, j, d)] = bB; t.b2[kidx(q, i, d)] = b2; }
   }
 }
+
+#if LIN_SPLIT_TMA && !defined(RELEM_HOST_EMU)
+// ---- bulk-copy (TMA) primitives, sm_90+ PTX
+RDEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+RDEV void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+RDEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+RDEV void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+RDEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#endif
 
 // ================================================================================= coupled passes
 struct CTabs {
@@ -589,13 +574,20 @@ struct WarpLin {
   double* pcnt;   // pair-emission posterior sums [n_pair*25] of channel 0 in the slot header (global, RED)
   unsigned pstride;  // channel stride of pcnt
   int n_max;
+  double* stage;             // LIN_SPLIT_TMA: [LIN_TMA_STAGES][2][S] staged operand vectors of the split gather
+  unsigned long long* bar;   // its mbarrier
+  unsigned phase;            // parity of the next completion
 };
 // inside = true: only what the inside pass needs (no outside staging, no counts)
 RHD int warp_lin_bytes(int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside) {
   int n = inside ? (S + n_max + 3 * LIN_CAP) * 8
                  : (S + nch * S + 2 * nch * n_max + 3 * LIN_CAP + nch * 5 * (n_right + n_left)) * 8;
   n += (2 * LIN_CAP + Wmax + 4) * 4;
-  return (n + 15) & ~15;
+  n = (n + 15) & ~15;
+#if LIN_SPLIT_TMA
+  if (inside) n += LIN_TMA_STAGES * 2 * S * 8 + 16;   // staging buffer (16-byte aligned: n is) + mbarrier
+#endif
+  return n;
 }
 RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside) {
   WarpLin w;
@@ -613,9 +605,19 @@ RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n
   w.bi = ip; ip += LIN_CAP;
   w.bj = ip; ip += LIN_CAP;
   w.kbuf = ip;
-  (void)Wmax;
   w.pcnt = nullptr;
   w.n_max = n_max;
+  w.stage = nullptr; w.bar = nullptr; w.phase = 0u;
+#if LIN_SPLIT_TMA
+  if (inside) {
+    int n = (S + n_max + 3 * LIN_CAP) * 8 + (2 * LIN_CAP + Wmax + 4) * 4;
+    n = (n + 15) & ~15;
+    w.stage = (double*)(base + n);
+    w.bar = (unsigned long long*)(base + n + LIN_TMA_STAGES * 2 * S * 8);
+  }
+#else
+  (void)Wmax;
+#endif
   return w;
 }
 
@@ -884,6 +886,38 @@ RDEV void lin_in_B(const LinCtx& c, const CTabs& t, int i, int d, bool gP, bool 
     }
     const double* r1 = t.a1 + cidx(q, i, 0);
     const double* r2 = t.a2 + cidx(q, j, 0) + (unsigned)d * S;
+#if LIN_SPLIT_TMA && !defined(RELEM_HOST_EMU)
+    if ((S & 1) == 0) {
+      // staged: batches of up to LIN_TMA_STAGES split points; lane t of a batch issues the two bulk copies of its split
+      // point (1(i,u,.) and 2(u,j,.), S doubles each), lane 0 arms the barrier with the batch's byte count
+      const unsigned vb = (unsigned)S * 8u;
+      for (int a = lane; a < h.n_split; a += WARP_N) part[a] = 0.;
+      for (int t0 = 0; t0 < nk; t0 += LIN_TMA_STAGES) {
+        const int nb = nk - t0 < LIN_TMA_STAGES ? nk - t0 : LIN_TMA_STAGES;
+        w_sync();   // the previous batch has been consumed
+        if (lane == 0) mbar_expect_tx(w.bar, 2u * vb * (unsigned)nb);
+        w_sync();
+        if (lane < nb) {
+          const int u = w.kbuf[t0 + lane] * S;
+          bulk_g2s(w.stage + (2 * lane) * S, r1 + u, vb, w.bar);
+          bulk_g2s(w.stage + (2 * lane + 1) * S, r2 - u, vb, w.bar);
+        }
+        mbar_wait(w.bar, w.phase);
+        w.phase ^= 1u;
+        for (int a = lane; a < h.n_split; a += WARP_N) {
+          const int sl = ld_ro(h.sp_l + a), sr = ld_ro(h.sp_r + a);
+          double v0 = 0., v1 = 0.;
+          int tt = 0;
+          for (; tt + 1 < nb; tt += 2) {
+            v0 += w.stage[(2 * tt) * S + sl] * w.stage[(2 * tt + 1) * S + sr];
+            v1 += w.stage[(2 * tt + 2) * S + sl] * w.stage[(2 * tt + 3) * S + sr];
+          }
+          if (tt < nb) v0 += w.stage[(2 * tt) * S + sl] * w.stage[(2 * tt + 1) * S + sr];
+          part[a] += v0 + v1;
+        }
+      }
+    } else
+#endif
     for (int a = lane; a < h.n_split; a += WARP_N) {
       const double* p1 = r1 + ld_ro(h.sp_l + a);
       const double* p2 = r2 + ld_ro(h.sp_r + a);

@@ -395,8 +395,8 @@ RDEV void cta_viterbi_forward(const ModelView& m, const SeqView& q, double* tab,
     rg.cells(d, ncell, nb, na);
     const int nbg = nb + na, npack = (nbg + WARP_N - 1) / WARP_N, nfull = ncell - nbg;
     // static hand-out: the (at most a few) long packs go to different warps first, the full cells follow round robin.
-    // (Handing units out through a shared atomic counter was tried and gave wrong tables on the B200 although every
-    // value checked out when re-derived in place -- not understood, dropped; see profiles/r2_viterbi.md.)
+    // Tried and dropped (profiles/r2_viterbi.md): units through a shared atomic counter (wrong tables on the device,
+    // not understood); one warp per single-state cell with lanes over candidates (correct, 1.5x slower than the packs).
     for (int u = warp_id(); u < npack + nfull; u += n_warps()) {
       if (u < npack) {
         const int t = u * WARP_N + lane;

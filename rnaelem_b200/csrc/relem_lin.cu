@@ -48,7 +48,7 @@ struct LinLayout {
   unsigned long long stride;  // doubles per slot
   unsigned long long aP, aE, aM, a1, a2, aLl, aLr, aO;
   unsigned long long bP, bEl, bEr, bM, bBl, bBr, b2, bL, bO, bch, boch;
-  unsigned long long kP, kE, kM, k1, k2, kO, kbP, kbE, kbM, kbBl, kbBr, kb2, kbO, kPm, kbEm, kPn, kPu, kbEn, kbEu;
+  unsigned long long kP, kE, kM, k1, k2, kO, kbP, kbE, kbM, kbBl, kbBr, kb2, kbO, kPm, kbEm;
   // per-slot header
   unsigned long long hdr;    // [16]: Z^tt, Z^tf, Z^ft, bad, canonical pair count, L, ys, -, EH[nch*2]
   unsigned long long wsf;    // [Lmax+1] exp(position weight)
@@ -83,7 +83,6 @@ static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int nc
   lay.kbP = take(cells); lay.kbE = take(cells); lay.kbM = take(cells); lay.kbBl = take(cells); lay.kbBr = take(cells);
   lay.kb2 = take(cells); lay.kbO = take(Lmax + 1);
   lay.kPm = take(cells); lay.kbEm = take(cells);
-  lay.kPn = take(cells); lay.kPu = take(cells); lay.kbEn = take(cells); lay.kbEu = take(cells);
   lay.hdr = take(16);
   lay.wsf = take(Lmax + 1);
   lay.cnt = take((unsigned long long)nch * lay.ncnt);
@@ -194,7 +193,6 @@ RDEV CTabs lin_tabs(const LinLayout& lay, double* slot) {
 RDEV K0Tabs lin_k0tabs(const LinLayout& lay, double* slot, const double* G) {
   K0Tabs t0;
   t0.Pm = slot + lay.kPm; t0.bEm = slot + lay.kbEm; t0.G = G;
-  t0.Pn = slot + lay.kPn; t0.Pu = slot + lay.kPu; t0.bEn = slot + lay.kbEn; t0.bEu = slot + lay.kbEu;
   t0.eO = slot + lay.expo; t0.fO = t0.eO + (lay.Lmax + 2);
   t0.P = slot + lay.kP; t0.E = slot + lay.kE; t0.M = slot + lay.kM; t0.o1 = slot + lay.k1; t0.o2 = slot + lay.k2;
   t0.O = slot + lay.kO; t0.bP = slot + lay.kbP; t0.bE = slot + lay.kbE; t0.bM = slot + lay.kbM;
@@ -211,10 +209,8 @@ LIN_KERNEL(LIN_THREADS, 8) relem_lin_gtab_kernel(LinKArgs a LIN_SMEM_ARG) {
   for (int t = CTA_TID; t < 1024; t += CTA_NTH) {
     int u1 = t >> 5, u2 = t & 31, du = u1 > u2 ? u1 - u2 : u2 - u1;
     double v = 0.;
-    if (u1 >= 1 && u2 >= 1 && u1 + u2 <= 30)
+    if (u1 >= 3 && u2 >= 3 && u1 + u2 <= 30)
       v = ld_ro(LC.el.internal + u1 + u2) * ld_ro(LC.el.ninio + du) * a.k0pow[u1 + u2];
-    else if ((u1 == 0 || u2 == 0) && u1 + u2 >= 2 && u1 + u2 <= 30)
-      v = ld_ro(LC.el.bulge + u1 + u2) * a.k0pow[u1 + u2];   // bulge of length u1+u2 (row / column 0)
     G[t] = v;
   }
 }
@@ -349,6 +345,15 @@ relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
   const LinHMM& h = LC.h;
   if (PH >= PH_IN_L && PH <= PH_IN_E) {
     WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + w0 * lay.warp_bytes_in, q.S, lay.Wmax, 1, h.n_max, 0, 0, true);
+#if LIN_SPLIT_TMA && !defined(RELEM_HOST_EMU)
+    if (PH == PH_IN_B) {   // the warp's bulk-copy barrier: one arrival (the lane that arms it) per batch
+      if (lane_id() == 0) {
+        mbar_init(w.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      w_sync();
+    }
+#endif
     for (int i = i0 + w0; i < i1; i += nw) {
       if (PH == PH_IN_L) lin_in_L(c, t, i, d, w);
       if (PH == PH_IN_P) { if (ok_P(q, i, d)) lin_in_P(c, t, i, d, w); }
