@@ -26,7 +26,9 @@ struct SlotLayout {
   // dynamic shared memory carve-up (byte offsets)
   int sm_x, sm_sp3, sm_sp4, sm_sp6, sm_bp, sm_lf, sm_bp2, sm_en, sm_pys, sm_pyi, sm_pye, sm_red, sm_ctr, sm_warp, warp_bytes,
       sm_total;
-  int sm_vit_ctr, sm_vit_warp, vit_warp_bytes, sm_total_vit, vit_n_max;   // Viterbi kernel: see make_layout
+  // Viterbi kernel (its own carve-up, see make_layout): claim slot, VitSeq[R], R per-sequence blocks (bases, special
+  // hairpins, two masks), one VitWarp slice per warp
+  int sm_vit_claim, sm_vit_ctx, sm_vit_seq, vit_seq_bytes, vit_R, sm_vit_warp, vit_warp_bytes, sm_total_vit, vit_n_max;
 };
 
 struct BppOut {
@@ -549,59 +551,98 @@ struct ExtMasks {
 #define RELEM_VIT_KERNEL __global__ void __launch_bounds__(RELEM_VIT_THREADS, 512 / RELEM_VIT_THREADS)
 #endif
 RELEM_VIT_KERNEL relem_viterbi_kernel(ModelView m, BatchView b, SlotLayout lay, double* scratch, int* queue, const int* n2s,
-                                  ScanOut out, ExtMasks em, const unsigned char* flag RELEM_SMEM_ARG) {
+                                      ScanOut out, ExtMasks em, const unsigned char* flag RELEM_SMEM_ARG) {
 #ifndef RELEM_HOST_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
-  Smem sm = carve(smem_raw, lay);
-  double* slot = scratch + (unsigned long long)RELEM_BLOCK_IDX * lay.stride;
-  const int S = m.h.S;
+  const int S = m.h.S, R = lay.vit_R;
   const DevHMM& h = m.h;
+  int* claim_sh = (int*)(smem_raw + lay.sm_vit_claim);
+  VitSeq* seqs = (VitSeq*)(smem_raw + lay.sm_vit_ctx);
+  VitWarp vw = vit_warp_carve(smem_raw + lay.sm_vit_warp + warp_id() * lay.vit_warp_bytes, S, lay.vit_n_max);
   // background states of cells outside the motif region (StartEndConstraint, dp_enum.cuh)
   int s_bgM = -1;
   for (int s = 0; s < S; ++s)
     if (ld_ro(h.st_l + s) == h.M - 1 && ld_ro(h.st_r + s) == h.M - 1) s_bgM = s;
+  const int mask_bytes = ((lay.Lmax + 1) * lay.mw * 4 + 15) & ~15, row_bytes = (lay.Lmax + 2 + 15) & ~15;
   for (;;) {
-    int qi = claim(queue, (int*)(sm.red + 40));
-    if (qi >= em.count) break;
-    int n = b.order[em.base + qi];
-    if (flag[n]) continue;   // left the fp64 range in the linear-space pass: the full log-space kernel redoes it
-    SeqView q;
-    q.S = S;
-    long long o = b.off[n];
-    const int L = (int)(b.off[n + 1] - o);
-    const int W = L < m.en.max_span ? L : m.en.max_span;
-    const int C = W - 7 < m.en.max_iloop ? W - 7 : m.en.max_iloop;
-    q.L = L; q.W = W; q.C = C; q.W1 = W + 1; q.cells = (unsigned)(L + 1) * (unsigned)(W + 1);
-    q.mw = lay.mw; q.min_pair = 5; q.min_multi = 10;
-    q.x = sm.x; q.bp = sm.bp; q.lf = sm.lf; q.sp3 = sm.sp3; q.sp4 = sm.sp4; q.sp6 = sm.sp6;
-    q.ws = b.ws + o;
-    for (int t = CTA_TID; t < L; t += CTA_NTH) sm.x[t] = b.seq[o + t];
-    if (CTA_TID == 0) sm.x[L] = 0;
-    // the four masks the linear-space passes left in the slot header: pairs and left-ends by left end (copied to
-    // shared memory: every gate test reads them) and by right end (read in place: candidate scans only)
-    const unsigned* g = (const unsigned*)(em.scratch + (unsigned long long)qi * em.stride + em.masks_off);
-    for (int t = CTA_TID; t < (L + 1) * lay.mw; t += CTA_NTH) { sm.bp[t] = g[t]; sm.lf[t] = g[em.mask_words + t]; }
-    q.bpr = g + 2 * (size_t)em.mask_words; q.lfr = g + 3 * (size_t)em.mask_words;
-    CTA_SYNC();
-    cta_special_hairpins(m.en, sm.x, L, sm.sp3, sm.sp4, sm.sp6);
-    double* emit0 = slot + lay.emit0; double* emitT = slot + lay.emitT;
-    q.emit0 = emit0; q.emitT = emitT;
-    cta_emit_tables(m, q, emit0, emitT);
-    for (int t = CTA_TID; t < L; t += CTA_NTH) { out.psihat[o + t] = 0; out.rss[o + t] = ' '; }
-    CTA_SYNC();
-    double* tab = slot + lay.tabA; double* otab = slot + lay.otab;
-    StartEndConstraint se; se.ys = out.Ys[n]; se.ye = out.Ye[n];
-    VitRegion rg;
-    rg.ys = se.ys; rg.ye = se.ye; rg.s_bg0 = h.s00; rg.s_bgM = s_bgM;
-    rg.on = h.s00 >= 0 && s_bgM >= 0 && se.ys >= 0 && se.ye >= se.ys;
-    VitWarp vw = vit_warp_carve(smem_raw + lay.sm_vit_warp + warp_id() * lay.vit_warp_bytes, S, lay.vit_n_max);
-    cta_viterbi_forward(m, q, tab, otab, se, rg, vw);
+    // ---- claim the next R sequences of the chunk
     if (CTA_TID == 0) {
-      double a = h.s0M2 >= 0 ? otab[L * S + h.s0M2] : NINF;
-      double c = h.s0M1 >= 0 ? otab[L * S + h.s0M1] : NINF;
-      int s0 = (a < c) ? h.s0M1 : h.s0M2;
-      if (s0 >= 0) vit_trace_back(m, q, tab, otab, se, rg, n2s, (int*)(slot + lay.stack), s0, out.psihat + o, out.rss + o);
+#ifdef RELEM_HOST_EMU
+      *claim_sh = *queue; *queue += R;
+#else
+      *claim_sh = atomicAdd(queue, R);
+#endif
+    }
+    CTA_SYNC();
+    const int q0 = *claim_sh;
+    CTA_SYNC();
+    if (q0 >= em.count) break;
+    const int nr = em.count - q0 < R ? em.count - q0 : R;
+    int Wmax = 0;
+    // ---- set-up of every sequence of the batch (all threads)
+    for (int r = 0; r < nr; ++r) {
+      VitSeq& z = seqs[r];
+      const int qi = q0 + r, n = b.order[em.base + qi];
+      unsigned char* blk = smem_raw + lay.sm_vit_seq + r * lay.vit_seq_bytes;
+      unsigned char* x = blk;
+      signed char* sp3 = (signed char*)(blk + row_bytes);
+      signed char* sp4 = (signed char*)(blk + 2 * row_bytes);
+      signed char* sp6 = (signed char*)(blk + 3 * row_bytes);
+      unsigned* bp = (unsigned*)(blk + 4 * row_bytes);
+      unsigned* lf = (unsigned*)(blk + 4 * row_bytes + mask_bytes);
+      double* slot = scratch + ((unsigned long long)RELEM_BLOCK_IDX * R + r) * lay.stride;
+      const long long o = b.off[n];
+      const int L = (int)(b.off[n + 1] - o);
+      const int W = L < m.en.max_span ? L : m.en.max_span;
+      const int C = W - 7 < m.en.max_iloop ? W - 7 : m.en.max_iloop;
+      // the four masks the linear-space passes left in the slot header: pairs and left-ends by left end (copied to
+      // shared memory: every gate test reads them) and by right end (read in place: candidate scans only)
+      const unsigned* g = (const unsigned*)(em.scratch + (unsigned long long)qi * em.stride + em.masks_off);
+      if (CTA_TID == 0) {
+        // left the fp64 range in the linear-space pass: the full log-space kernel redoes it
+        z.n = flag[n] ? -1 : n;
+        z.o = o;
+        SeqView& q = z.q;
+        q.S = S; q.L = L; q.W = W; q.C = C; q.W1 = W + 1; q.cells = (unsigned)(L + 1) * (unsigned)(W + 1);
+        q.mw = lay.mw; q.min_pair = 5; q.min_multi = 10;
+        q.x = x; q.bp = bp; q.lf = lf; q.sp3 = sp3; q.sp4 = sp4; q.sp6 = sp6;
+        q.ws = b.ws + o;
+        q.bpr = g + 2 * (size_t)em.mask_words; q.lfr = g + 3 * (size_t)em.mask_words;
+        q.emit0 = slot + lay.emit0; q.emitT = slot + lay.emitT;
+        z.tab = slot + lay.tabA; z.otab = slot + lay.otab; z.stack = (int*)(slot + lay.stack);
+        z.se.ys = out.Ys[n]; z.se.ye = out.Ye[n];
+        z.rg.ys = z.se.ys; z.rg.ye = z.se.ye; z.rg.s_bg0 = h.s00; z.rg.s_bgM = s_bgM;
+        z.rg.on = h.s00 >= 0 && s_bgM >= 0 && z.se.ys >= 0 && z.se.ye >= z.se.ys;
+      }
+      if (flag[n]) continue;
+      if (W > Wmax) Wmax = W;
+      for (int t = CTA_TID; t < L; t += CTA_NTH) { x[t] = b.seq[o + t]; out.psihat[o + t] = 0; out.rss[o + t] = ' '; }
+      if (CTA_TID == 0) x[L] = 0;
+      for (int t = CTA_TID; t < (L + 1) * lay.mw; t += CTA_NTH) { bp[t] = g[t]; lf[t] = g[em.mask_words + t]; }
+    }
+    CTA_SYNC();
+    for (int r = 0; r < nr; ++r) {
+      const VitSeq& z = seqs[r];
+      if (z.n < 0) continue;
+      cta_special_hairpins(m.en, z.q.x, z.q.L, (signed char*)z.q.sp3, (signed char*)z.q.sp4, (signed char*)z.q.sp6);
+      cta_emit_tables(m, z.q, (double*)z.q.emit0, (double*)z.q.emitT);
+    }
+    CTA_SYNC();
+    // ---- band sweep of the whole batch, then exterior row + traceback of sequence r on warp r
+    cta_viterbi_band<StartEndConstraint>(m, seqs, nr, Wmax, vw);
+    for (int r = warp_id(); r < nr; r += n_warps()) {
+      const VitSeq& z = seqs[r];
+      if (z.n < 0) continue;
+      warp_viterbi_exterior<StartEndConstraint>(m, z);
+      if (lane_id() == 0) {
+        const int L = z.q.L;
+        double a = h.s0M2 >= 0 ? z.otab[L * S + h.s0M2] : NINF;
+        double c = h.s0M1 >= 0 ? z.otab[L * S + h.s0M1] : NINF;
+        int s0 = (a < c) ? h.s0M1 : h.s0M2;
+        if (s0 >= 0) vit_trace_back(m, z.q, z.tab, z.otab, z.se, z.rg, n2s, z.stack, s0, out.psihat + z.o, out.rss + z.o);
+      }
+      w_sync();
     }
     CTA_SYNC();
   }

@@ -579,17 +579,21 @@ struct WarpLin {
   unsigned phase;            // parity of the next completion
 };
 // inside = true: only what the inside pass needs (no outside staging, no counts)
-RHD int warp_lin_bytes(int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside) {
+// staged = true: room for the bulk-copy staging buffer of the split gather (inside B only)
+RHD int warp_lin_bytes(int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside, bool staged = false) {
   int n = inside ? (S + n_max + 3 * LIN_CAP) * 8
                  : (S + nch * S + 2 * nch * n_max + 3 * LIN_CAP + nch * 5 * (n_right + n_left)) * 8;
   n += (2 * LIN_CAP + Wmax + 4) * 4;
   n = (n + 15) & ~15;
 #if LIN_SPLIT_TMA
-  if (inside) n += LIN_TMA_STAGES * 2 * S * 8 + 16;   // staging buffer (16-byte aligned: n is) + mbarrier
+  if (inside && staged) n += LIN_TMA_STAGES * 2 * S * 8 + 16;   // staging buffer (16-byte aligned: n is) + mbarrier
+#else
+  (void)staged;
 #endif
   return n;
 }
-RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside) {
+RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside,
+                            bool staged = false) {
   WarpLin w;
   double* p = (double*)base;
   w.curA = p; p += S;
@@ -609,14 +613,14 @@ RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n
   w.n_max = n_max;
   w.stage = nullptr; w.bar = nullptr; w.phase = 0u;
 #if LIN_SPLIT_TMA
-  if (inside) {
+  if (inside && staged) {
     int n = (S + n_max + 3 * LIN_CAP) * 8 + (2 * LIN_CAP + Wmax + 4) * 4;
     n = (n + 15) & ~15;
     w.stage = (double*)(base + n);
     w.bar = (unsigned long long*)(base + n + LIN_TMA_STAGES * 2 * S * 8);
   }
 #else
-  (void)Wmax;
+  (void)Wmax; (void)staged;
 #endif
   return w;
 }
@@ -887,7 +891,7 @@ RDEV void lin_in_B(const LinCtx& c, const CTabs& t, int i, int d, bool gP, bool 
     const double* r1 = t.a1 + cidx(q, i, 0);
     const double* r2 = t.a2 + cidx(q, j, 0) + (unsigned)d * S;
 #if LIN_SPLIT_TMA && !defined(RELEM_HOST_EMU)
-    if ((S & 1) == 0) {
+    if ((S & 1) == 0 && w.stage) {
       // staged: batches of up to LIN_TMA_STAGES split points; lane t of a batch issues the two bulk copies of its split
       // point (1(i,u,.) and 2(u,j,.), S doubles each), lane 0 arms the barrier with the batch's byte count
       const unsigned vb = (unsigned)S * 8u;

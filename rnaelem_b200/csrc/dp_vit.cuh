@@ -380,67 +380,74 @@ RDEV void vit_full_cell(const ModelView& m, const SeqView& q, double* tab, const
   }
 }
 
-// forward pass of one sequence by one CTA; one barrier per diagonal.  Units of a diagonal: a pack of WARP_N single-state
-// cells (one thread each), or one full cell (the whole warp).
+// ---- a CTA works on a BATCH of sequences at once.  The band sweep needs one CTA barrier per diagonal, the exterior
+// row is a serial recurrence over the positions and the traceback is one thread: with one sequence per CTA half of the
+// warp time was spent waiting at those barriers (profiles/r2_viterbi.md).  With R sequences per CTA the units of a
+// diagonal of all R sequences share one barrier, and exterior row and traceback of sequence r run on warp r alone
+// (warp-level synchronisation only), R of them side by side.
+struct VitSeq {
+  SeqView q;
+  double* tab;
+  double* otab;
+  int* stack;
+  StartEndConstraint se;
+  VitRegion rg;
+  int n;          // sequence index in the batch view, -1 = empty place
+  long long o;    // offset of its bases
+};
+
 template <class CON>
-RDEV void cta_viterbi_forward(const ModelView& m, const SeqView& q, double* tab, double* otab, const CON& con,
-                              const VitRegion& rg, VitWarp& w) {
-  const int S = q.S, L = q.L, W = q.W;
-  const int lane = lane_id();
-  VitRegion off = rg;
-  off.on = false;   // a single-state cell reads single-state entries only: no pruning test needed on its reads
-  for (int d = 0; d <= W; ++d) {
-    const int ncell = L + 1 - d;
-    int nb, na;
-    rg.cells(d, ncell, nb, na);
-    const int nbg = nb + na, npack = (nbg + WARP_N - 1) / WARP_N, nfull = ncell - nbg;
-    // static hand-out: the (at most a few) long packs go to different warps first, the full cells follow round robin.
-    // Tried and dropped (profiles/r2_viterbi.md): units through a shared atomic counter (wrong tables on the device,
-    // not understood); one warp per single-state cell with lanes over candidates (correct, 1.5x slower than the packs).
-    for (int u = warp_id(); u < npack + nfull; u += n_warps()) {
-      if (u < npack) {
-        const int t = u * WARP_N + lane;
-        if (t < nbg) {
-          const bool lead = t < nb;
-          vit_cell_state(m, q, tab, otab, con, off, lead ? t : ncell - na + (t - nb), d, lead ? rg.s_bg0 : rg.s_bgM);
-        }
-      } else {
-        vit_full_cell(m, q, tab, con, rg, nb + (u - npack), d, w);
-#ifdef RELEM_VIT_CHECK
-        // debug build: every value of the cell against the reference-order enumerators (the lane-per-state mapping)
-        {
-          const int ci = nb + (u - npack);
-          w_sync();
-          for (int s = lane; s < S; s += WARP_N) {
-            double got[NPLANE];
-            for (int pl = 0; pl < NPLANE; ++pl) got[pl] = tab[band_idx(q, pl, ci, d, s)];
-            vit_cell_state(m, q, tab, otab, con, rg, ci, d, s);
-            const bool g[NPLANE] = {ok_P(q, ci, d), ok_E(q, ci, d), ok_M(q, ci, d), ok_B(q, ci, d), ok_B(q, ci, d), ok_B(q, ci, d), true};
-            for (int pl = 0; pl < NPLANE; ++pl) {
-              const double want = tab[band_idx(q, pl, ci, d, s)];
-              if (g[pl] && (pl == PL_L || d >= 3) && !(got[pl] == want))
-                printf("VITCHECK cell (%d,%d) plane %d state %d: %.17g vs %.17g\n", ci, d, pl, s, got[pl], want);
-            }
+RDEV void cta_viterbi_band(const ModelView& m, const VitSeq* seqs, int nr, int Wmax, VitWarp& w) {
+  const int lane = lane_id(), w0 = warp_id(), nw = n_warps();
+  for (int d = 0; d <= Wmax; ++d) {
+    int ubase = 0;   // units of this diagonal handed out so far (round robin over the warps, across the sequences)
+    for (int r = 0; r < nr; ++r) {
+      const VitSeq& z = seqs[r];
+      if (z.n < 0 || d > z.q.W) continue;
+      const SeqView q = z.q;   // private copy: the shared-memory original would be re-read at every use
+      const int ncell = q.L + 1 - d;
+      int nb, na;
+      z.rg.cells(d, ncell, nb, na);
+      const int nbg = nb + na, npack = (nbg + WARP_N - 1) / WARP_N, nfull = ncell - nbg;
+      VitRegion off = z.rg;
+      off.on = false;   // a single-state cell reads single-state entries only: no pruning test needed on its reads
+      // static hand-out: the long packs first, the full cells follow.  Tried and dropped (profiles/r2_viterbi.md): units
+      // through a shared atomic counter (wrong tables on the device, not understood); one warp per single-state cell
+      // with lanes over candidates (correct, 1.5x slower than the packs).
+      int u = (w0 - ubase % nw + nw) % nw;
+      for (; u < npack + nfull; u += nw) {
+        if (u < npack) {
+          const int t = u * WARP_N + lane;
+          if (t < nbg) {
+            const bool lead = t < nb;
+            vit_cell_state(m, q, z.tab, z.otab, (const CON&)z.se, off, lead ? t : ncell - na + (t - nb), d,
+                           lead ? z.rg.s_bg0 : z.rg.s_bgM);
           }
-          w_sync();
+        } else {
+          vit_full_cell(m, q, z.tab, (const CON&)z.se, z.rg, nb + (u - npack), d, w);
         }
-#endif
       }
+      ubase += npack + nfull;
     }
     CTA_SYNC();
   }
-  // exterior recurrence (never pruned: S values per position)
-  for (int t = CTA_TID; t < S; t += CTA_NTH) otab[t] = (t == m.h.s00) ? 0. : NINF;
-  CTA_SYNC();
+}
+
+// exterior recurrence of one sequence by ONE warp (never pruned: S values per position)
+template <class CON> RDEV void warp_viterbi_exterior(const ModelView& m, const VitSeq& z) {
+  const SeqView q = z.q;
+  const int S = q.S, L = q.L, lane = lane_id();
+  for (int t = lane; t < S; t += WARP_N) z.otab[t] = (t == m.h.s00) ? 0. : NINF;
+  w_sync();
   for (int j = 1; j <= L; ++j) {
-    for (int s = CTA_TID; s < S; s += CTA_NTH) {
+    for (int s = lane; s < S; s += WARP_N) {
       VitV<CON> v;
-      v.tab = tab; v.otab = otab; v.con = con; v.rg = rg;
+      v.tab = z.tab; v.otab = z.otab; v.con = (const CON&)z.se; v.rg = z.rg;
       v.init();
       enum_O(m, q, j, s, v);
-      otab[j * S + s] = v.best;
+      z.otab[j * S + s] = v.best;
     }
-    CTA_SYNC();
+    w_sync();
   }
 }
 

@@ -260,15 +260,18 @@ static void apply_mode(relem_ctx* c) {
 
 // choose the number of resident CTAs (= scratch slots) and make sure the scratch fits
 int plan_launch(relem_ctx* c, const relem_batch* b, int nch, bool coupled, const void* kernel, Launch& L,
-                int max_n = 1 << 30, int threads = RELEM_CTA_THREADS) {
+                int max_n = 1 << 30, int threads = RELEM_CTA_THREADS, bool kernel_is_viterbi = false) {
   int S = c->flat.S, M = c->flat.M;
   L.c = c;
   const FlatHMM& f = c->flat;
   const size_t nlm = std::max(std::max(std::max(f.right_idx.size(), f.left_idx.size()), std::max(f.pair_idx.size(), f.split_left.size())),
                               f.quad_s1.size());
-  L.lay = make_layout(std::max(1, b->Lmax), eff_span(c), S, M, c->n_theta, nch, coupled, (int)nlm);
-  const bool vit = threads == RELEM_VIT_THREADS;
+  const bool vit = kernel_is_viterbi;
+  int vit_cap = 0;   // limit on the sequences per Viterbi CTA (0 = what shared memory allows)
+  if (const char* e = std::getenv("RELEM_VIT_READS")) vit_cap = std::max(1, std::atoi(e));
+  L.lay = make_layout(std::max(1, b->Lmax), eff_span(c), S, M, c->n_theta, nch, coupled, (int)nlm, vit ? -(vit_cap + 1) : 0);
   const int sm_bytes = vit ? L.lay.sm_total_vit : L.lay.sm_total;
+  const int R = vit ? L.lay.vit_R : 1;   // slots per CTA
   unsigned long long band = (unsigned long long)NPLANE * (b->Lmax + 1) * (L.lay.Wmax + 1) * (coupled ? S : 1);
   if (band >= (1ull << 31)) return fail(c, RELEM_EINVAL, "band table of one sequence exceeds 2^31 entries");
 #ifdef RELEM_HOST_EMU
@@ -285,11 +288,12 @@ int plan_launch(relem_ctx* c, const relem_batch* b, int nch, bool coupled, const
   size_t avail = free_b + c->d_scratch.bytes;
   size_t per = L.lay.stride * sizeof(double);
   long long by_mem = (long long)((avail * 0.85) / (double)per);
-  L.nslots = (int)std::min<long long>(std::min<long long>(std::min(b->nseq, max_n), (long long)c->sm_count * occ), by_mem);
+  // nslots = resident CTAs; each owns R slots
+  L.nslots = (int)std::min<long long>(std::min<long long>((std::min(b->nseq, max_n) + R - 1) / R, (long long)c->sm_count * occ), by_mem / R);
   if (const char* e = std::getenv("RELEM_MAX_SLOTS")) L.nslots = std::min(L.nslots, std::max(1, std::atoi(e)));
   if (L.nslots < 1) return fail(c, RELEM_ENOMEM, "not enough device memory for one sequence slot");
 #endif
-  if (!c->d_scratch.reserve((size_t)L.nslots * L.lay.stride * sizeof(double)))
+  if (!c->d_scratch.reserve((size_t)L.nslots * R * L.lay.stride * sizeof(double)))
     return fail(c, RELEM_ENOMEM, "scratch allocation failed");
   if (!c->d_queue.reserve(sizeof(int)) || !Dev::zero(c->d_queue.p, sizeof(int)))
     return fail(c, RELEM_ENOMEM, "queue allocation failed");
@@ -855,9 +859,9 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
   // when a sequence actually falls back to it
   Launch L;
 #ifdef RELEM_HOST_EMU
-  rc = plan_launch(c, b, 1, true, nullptr, L);
+  rc = plan_launch(c, b, 1, true, nullptr, L, 1 << 30, RELEM_VIT_THREADS, true);
 #else
-  rc = plan_launch(c, b, 1, true, (const void*)relem_viterbi_kernel, L, 1 << 30, RELEM_VIT_THREADS);
+  rc = plan_launch(c, b, 1, true, (const void*)relem_viterbi_kernel, L, 1 << 30, RELEM_VIT_THREADS, true);
 #endif
   if (rc) return rc;
   size_t tl = (size_t)b->total_len;
@@ -921,7 +925,8 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       v.ev.push_back(e0); v.ev.push_back(e1);
       cudaEventRecord(e0, st);
-      relem_viterbi_kernel<<<std::min(v.L->nslots, cv.count), RELEM_VIT_THREADS, v.L->lay.sm_total_vit, st>>>(
+      relem_viterbi_kernel<<<std::min(v.L->nslots, (cv.count + v.L->lay.vit_R - 1) / v.L->lay.vit_R), RELEM_VIT_THREADS,
+                             v.L->lay.sm_total_vit, st>>>(
           v.m, v.bv, v.L->lay, c->d_scratch.as<double>(), c->d_queue.as<int>(), c->d_n2s.as<int>(), v.so, em,
           c->d_flag.as<unsigned char>());
       cudaEventRecord(e1, st);
@@ -961,11 +966,14 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
     }
   }
   if (n_fallback > 0) {
+    // the all-in-one kernel has its own (full) slot layout
 #ifndef RELEM_HOST_EMU
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // the scratch may be re-allocated below
     rc = plan_launch(c, b, 1, true, (const void*)relem_scan_kernel, L, n_fallback);
-    if (rc) return rc;
+#else
+    rc = plan_launch(c, b, 1, true, nullptr, L, n_fallback);
 #endif
+    if (rc) return rc;
     if (!Dev::zero(c->d_queue.p, sizeof(int))) return fail(c, RELEM_ECUDA, "queue reset failed");
     Timer t(c, "relem_scan_kernel");
 #ifdef RELEM_HOST_EMU

@@ -58,7 +58,7 @@ struct LinLayout {
   unsigned long long post;   // scanner: linear start / inner / end posteriors, [Lmax+2] each
   unsigned long long expo;   // power-of-two exponents of the four exterior rows (K0 O, bO; coupled O, bO), [Lmax+2] each
   int Lmax, Wmax, mw, nch, ncnt, mask_words;
-  int sm_ctx, sm_misc, sm_pcnt, sm_warp, warp_bytes_in, warp_bytes_out;
+  int sm_ctx, sm_misc, sm_pcnt, sm_warp, warp_bytes_in, warp_bytes_inb, warp_bytes_out;
 };
 
 static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int nch) {
@@ -98,6 +98,7 @@ static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int nc
   lay.sm_pcnt = b;
   lay.sm_warp = b;
   lay.warp_bytes_in = warp_lin_bytes(h.S, Wmax, 1, h.n_max, 0, 0, true);
+  lay.warp_bytes_inb = warp_lin_bytes(h.S, Wmax, 1, h.n_max, 0, 0, true, true);   // inside B: + staging of the split gather
   lay.warp_bytes_out = warp_lin_bytes(h.S, Wmax, nch, h.n_max, h.n_right, h.n_left, false);
   return lay;
 }
@@ -296,6 +297,9 @@ template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot
 #ifndef LIN_MINB_SMALL
 #define LIN_MINB_SMALL 7
 #endif
+#ifndef LIN_STRIDED_SPARSE
+#define LIN_STRIDED_SPARSE 1   // A/B switch: cells of the sparse phases interleaved over the CTAs of a sequence
+#endif
 template <int PH, int NCH, int MODE = 0>
 LIN_KERNEL(LIN_THREADS, (PH <= PH_K0_OUT ? 8 : (PH == PH_OUT_B || PH == PH_IN_B) ? LIN_MINB_SPLIT : (PH == PH_OUT_L || PH == PH_OUT_EM || PH == PH_IN_P || PH == PH_IN_L) ? LIN_MINB_SMALL : 7))
 relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
@@ -330,8 +334,23 @@ relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
     const int lo = c.ys - 1 - d;
     if (i0 < lo) i0 = lo;
   }
-  if (i0 >= i1) return;
   const int w0 = warp_id(), nw = n_warps();
+  // Phases that touch few, unevenly spread cells (pairs and what they enclose): instead of a contiguous tile the CTA
+  // takes every ntile-th group of cells over the whole range, so stems do not pile up in one CTA (ncu: 19 % warps active
+  // in the interior-loop scatter with contiguous tiles, profiles/r2_phase_kernels.md).
+  constexpr bool kStrided = LIN_STRIDED_SPARSE && (PH == PH_IN_P || PH == PH_IN_E || PH == PH_OUT_EM || PH == PH_OUT_P ||
+                                                   PH == PH_OUT_ES || PH == PH_OUT_PQ);
+  int first = i0 + w0, step = nw;
+  if (kStrided) {
+    int r0 = 0, r1 = ncell;
+    if (PH >= PH_IN_L && PH <= PH_IN_E && a.win) {
+      r0 = c.ys - d > 0 ? c.ys - d : 0;
+      r1 = (c.ys + 1 < ncell - 1 ? c.ys + 1 : ncell - 1) + 1;
+    }
+    if (PH >= PH_OUT_EM && MODE == 2 && r0 < c.ys - 1 - d) r0 = c.ys - 1 - d;
+    first = r0 + tk * nw + w0; step = a.ntile * nw; i1 = r1;
+    if (r0 + tk * nw >= r1) return;
+  } else if (i0 >= i1) return;
   if (PH == PH_K0_IN || PH == PH_K0_OUT) {
     K0Tabs t0 = lin_k0tabs(lay, slot, a.k0pow + a.kp_n);
     for (int i = i0 + w0; i < i1; i += nw) {
@@ -344,7 +363,8 @@ relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
   CTabs t = lin_tabs(lay, slot);
   const LinHMM& h = LC.h;
   if (PH >= PH_IN_L && PH <= PH_IN_E) {
-    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + w0 * lay.warp_bytes_in, q.S, lay.Wmax, 1, h.n_max, 0, 0, true);
+    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + w0 * (PH == PH_IN_B ? lay.warp_bytes_inb : lay.warp_bytes_in), q.S, lay.Wmax,
+                               1, h.n_max, 0, 0, true, PH == PH_IN_B);
 #if LIN_SPLIT_TMA && !defined(RELEM_HOST_EMU)
     if (PH == PH_IN_B) {   // the warp's bulk-copy barrier: one arrival (the lane that arms it) per batch
       if (lane_id() == 0) {
@@ -354,7 +374,7 @@ relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
       w_sync();
     }
 #endif
-    for (int i = i0 + w0; i < i1; i += nw) {
+    for (int i = first; i < i1; i += step) {
       if (PH == PH_IN_L) lin_in_L(c, t, i, d, w);
       if (PH == PH_IN_P) { if (ok_P(q, i, d)) lin_in_P(c, t, i, d, w); }
       if (PH == PH_IN_B) {
@@ -375,7 +395,7 @@ relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
     w_sync();
     EhAcc<NCH> eh;
     for (int k = 0; k < NCH * 2; ++k) eh.v[k] = 0.;
-    for (int i = i0 + w0; i < i1; i += nw) {
+    for (int i = first; i < i1; i += step) {
       if (PH == PH_OUT_EM) {
         bool gE = ok_E(q, i, d), gM = ok_M(q, i, d);
         if (gE || gM) lin_out_EM<NCH, MODE>(c, t, i, d, gE, gM, w, eh);
@@ -751,7 +771,7 @@ void lin_state_destroy(LinState* s) {
 namespace {
 struct Runner {
   LinKArgs a;
-  int smem_in, smem_out, smem_small, smem_k0, smem_ext_in, smem_ext_out;
+  int smem_in, smem_inb, smem_out, smem_small, smem_k0, smem_ext_in, smem_ext_out;
   int launches = 0;
   int resident_ctas = 148 * 7;
   int cmax = 30;                   // longest unpaired flank of an interior loop: min(30, max_iloop, W - 7)
@@ -867,7 +887,7 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
     launch_phase<PH_IN_L, 1>(r, d, r.tile_d, r.smem_in);
     if (d >= 5) {
       launch_phase<PH_IN_P, 1>(r, d, r.tile_p, r.smem_in);
-      launch_phase<PH_IN_B, 1>(r, d, r.tile_d, r.smem_in);
+      launch_phase<PH_IN_B, 1>(r, d, r.tile_d, r.smem_inb);
     }
     if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, r.tile_e, r.smem_in);
   }
@@ -915,14 +935,14 @@ static void run_chunk_scan(Runner& r, bool filter, int NT) {
         launch_phase<PH_IN_L, 1>(r, d, r.tile_d, r.smem_in);
         if (d >= 5) {
           launch_phase<PH_IN_P, 1>(r, d, r.tile_p, r.smem_in);
-          launch_phase<PH_IN_B, 1>(r, d, r.tile_d, r.smem_in);
+          launch_phase<PH_IN_B, 1>(r, d, r.tile_d, r.smem_inb);
         }
         if (d >= 3) launch_phase<PH_IN_E, 1>(r, d, r.tile_e, r.smem_in);
       } else {
         launch_phase_win<PH_IN_L>(r, d, r.tile_d, r.smem_in);
         if (d >= 5) {
           launch_phase_win<PH_IN_P>(r, d, r.tile_p, r.smem_in);
-          launch_phase_win<PH_IN_B>(r, d, r.tile_d, r.smem_in);
+          launch_phase_win<PH_IN_B>(r, d, r.tile_d, r.smem_inb);
         }
         if (d >= 3) launch_phase_win<PH_IN_E>(r, d, r.tile_e, r.smem_in);
       }
@@ -995,6 +1015,7 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   r.smem_small = lay.sm_warp;
   r.smem_k0 = lay.sm_warp + LIN_WARPS * 128 * 4;
   r.smem_in = lay.sm_warp + LIN_WARPS * lay.warp_bytes_in;
+  r.smem_inb = lay.sm_warp + LIN_WARPS * lay.warp_bytes_inb;
   r.smem_out = lay.sm_warp + LIN_WARPS * lay.warp_bytes_out;
   r.smem_ext_in = lay.sm_warp + lay.warp_bytes_in;
   r.smem_ext_out = lay.sm_warp + lay.warp_bytes_out;
@@ -1028,7 +1049,7 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   st->k0pow = std::malloc(kp.size() * 8);
   std::memcpy(st->k0pow, kp.data(), kp.size() * 8);
   a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
-  r.smem.assign(std::max(std::max(r.smem_out, r.smem_in), NT * in.nch * 8 + 16) + 64, 0);
+  r.smem.assign(std::max(std::max(r.smem_out, r.smem_inb), NT * in.nch * 8 + 16) + 64, 0);
   LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
   for (int k = 0; k < nseq; k += emu_chunk) {
     // poison: the gather passes must never read an entry they did not write
@@ -1171,6 +1192,7 @@ int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_ch
   r.smem_small = lay.sm_warp;
   r.smem_k0 = lay.sm_warp + LIN_WARPS * 128 * 4;
   r.smem_in = lay.sm_warp + LIN_WARPS * lay.warp_bytes_in;
+  r.smem_inb = lay.sm_warp + LIN_WARPS * lay.warp_bytes_inb;
   r.smem_out = lay.sm_warp + LIN_WARPS * lay.warp_bytes_out;
   r.smem_ext_in = lay.sm_warp + lay.warp_bytes_in;
   r.smem_ext_out = lay.sm_warp + lay.warp_bytes_out;
@@ -1195,7 +1217,7 @@ int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_ch
   st->k0pow = std::malloc(kp.size() * 8);
   std::memcpy(st->k0pow, kp.data(), kp.size() * 8);
   a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
-  r.smem.assign(std::max(std::max(r.smem_out, r.smem_in), NT * 8 + 16) + 64, 0);
+  r.smem.assign(std::max(std::max(r.smem_out, r.smem_inb), NT * 8 + 16) + 64, 0);
   LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
   for (int k = 0; k < nseq; k += emu_chunk) {
     { double* p = (double*)st->scratch; for (size_t z = 0; z < per * emu_chunk / 8; ++z) p[z] = std::nan(""); }

@@ -130,3 +130,17 @@ def test_eval_emulated(name, emu_cli, tmp_path):
 @pytest.mark.parametrize("name", ["m0", "m1", "m2", "m3", "trna", "ragged", "synth200", "a2007_w150"])
 def test_eval_gpu(name, product_cli, tmp_path):
     _eval_case(product_cli, name, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus_failing_rank_does_not_hang(product_cli, tmp_path):
+    """a rank whose E-step fails must still enter the all-reduce (the failure travels as one more summed element):
+    the process ends with the rank's message instead of blocking the other rank in NCCL forever"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    c = clilib.MANIFEST["synth_adam"]
+    cmd = [product_cli, "-f", os.path.join(clilib.HERE, "golden", "_tmp", c["fastq"])] + c["args"] + \
+          ["--gpus", "2", "--out1", str(tmp_path / "m"), "--out2", str(tmp_path / "r"), "--out3", str(tmp_path / "i")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=dict(os.environ, RELEM_TEST_FAIL_RANK="1"))
+    assert p.returncode == 1 and "relem_estep failed on GPU 1" in p.stderr, p.stderr[-500:]
