@@ -548,7 +548,10 @@ struct ExtMasks {
 #ifdef RELEM_HOST_EMU
 #define RELEM_VIT_KERNEL inline void
 #else
-#define RELEM_VIT_KERNEL __global__ void __launch_bounds__(RELEM_VIT_THREADS, 512 / RELEM_VIT_THREADS)
+#ifndef RELEM_VIT_MINB
+#define RELEM_VIT_MINB (512 / RELEM_VIT_THREADS)
+#endif
+#define RELEM_VIT_KERNEL __global__ void __launch_bounds__(RELEM_VIT_THREADS, RELEM_VIT_MINB)
 #endif
 RELEM_VIT_KERNEL relem_viterbi_kernel(ModelView m, BatchView b, SlotLayout lay, double* scratch, int* queue, const int* n2s,
                                       ScanOut out, ExtMasks em, const unsigned char* flag RELEM_SMEM_ARG) {

@@ -61,7 +61,7 @@ inline SlotLayout make_layout(int Lmax, int max_span, int S, int M, int n_theta,
     lay.vit_warp_bytes = vit_warp_bytes(S, Wmax, lay.vit_n_max);
     const int fixed = 16 + nwarp * lay.vit_warp_bytes;
     int R = (100 * 1024 - fixed - 64) / (lay.vit_seq_bytes + (int)sizeof(VitSeq) + 16);
-    if (R > nwarp) R = nwarp;
+    if (R > nwarp / 2) R = nwarp / 2;   // measured: 4 per CTA = 8 per CTA = +4 % over one (profiles/r2_viterbi.md); fewer slots
     if (R < 1) R = 1;
     if (vit_reads_per_cta > 0 && R > vit_reads_per_cta) R = vit_reads_per_cta;
     lay.vit_R = R;
