@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "rnaelem_b200", "RNAelem")
 REF = os.path.join(ROOT, "oracle", "_ref", "RNAelem")
 # the first entries of the reference's pattern_list with a stem, plus its largest automaton
-PATTERNS4 = ["(...).....", "((...))...", "(.(...))..", ".....*.....", "((...*))...", "(....*)...."]
+PATTERNS4 = ["(...).....", "((...))...", "(.(...))..", "((...*))...", "(....*)....", ".....*....."]
 
 
 def write_fq(path, n, L, seed, plant="GGACUUCGGUCC", frac=0.5):
