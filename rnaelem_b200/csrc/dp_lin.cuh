@@ -1816,24 +1816,39 @@ RDEV void lin_out_ES(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w, 
       const double* bf = sl ? w.bf1 : w.bf0;
       double be[NCH];
       bool any = false;
-      for (int ch = 0; ch < NCH; ++ch) { be[ch] = t.bEl[ch * t.bch + il + s]; any = any || be[ch] != 0.; }
+      for (int ch = 0; ch < NCH; ++ch) { be[ch] = ld_ro(t.bEl + ch * t.bch + il + s); any = any || be[ch] != 0.; }
       if (!any) continue;
-      for (int pp = 0; pp < n; ++pp) {
-        const int k = w.bi[pp], l = w.bj[pp];
-        const double f = bf[pp];
-        if (f == 0.) continue;
-        const double ap = t.aP[cidx(q, l, l - k) + s1];
-        const double al = rL[(unsigned)(k - i) * S + s2], ar = rR[(unsigned)(j - l) * S + s3];
-        const double lr = al * ar, tsc = w.bt[pp];
-        const unsigned ip = cidx(q, k, l - k) + s1, ifl = r0 + (unsigned)(k - i) * S + s2, ifr = cidx(q, l, j - l) + s3;
-        for (int ch = 0; ch < NCH; ++ch) {
-          const double x = be[ch] * f;
-          if (x == 0.) continue;
-          const double xp = x * ap;
-          if (lr != 0.) red_add(t.bP + ch * t.bch + ip, x * lr);
-          if (k > i && xp * ar != 0.) red_add(t.bL + ch * t.bch + ifl, xp * ar);
-          if (l < j && xp * al != 0.) red_add(t.bL + ch * t.bch + ifr, xp * al);
-          eh.add(ch, sl, tsc * (xp * lr));
+      // four inner pairs at a time, all loads first: the REDs below may alias anything as far as the compiler knows,
+      // so a load issued after one waits for it -- with one pair per iteration every pair paid a full memory latency
+      // (the inside tables and b^E are not written by this kernel: read-only loads)
+      for (int p0 = 0; p0 < n; p0 += 4) {
+        double ap[4], al[4], ar[4], f[4];
+        int kk[4], ll[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pp = p0 + u;
+          const bool ok = pp < n;
+          kk[u] = ok ? w.bi[pp] : i; ll[u] = ok ? w.bj[pp] : j;
+          f[u] = ok ? bf[pp] : 0.;
+          ap[u] = ld_ro(t.aP + cidx(q, ll[u], ll[u] - kk[u]) + s1);
+          al[u] = ld_ro(rL + (unsigned)(kk[u] - i) * S + s2);
+          ar[u] = ld_ro(rR + (unsigned)(j - ll[u]) * S + s3);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (f[u] == 0.) continue;
+          const int k = kk[u], l = ll[u];
+          const double lr = al[u] * ar[u], tsc = w.bt[p0 + u];
+          const unsigned ip = cidx(q, k, l - k) + s1, ifl = r0 + (unsigned)(k - i) * S + s2, ifr = cidx(q, l, j - l) + s3;
+          for (int ch = 0; ch < NCH; ++ch) {
+            const double x = be[ch] * f[u];
+            if (x == 0.) continue;
+            const double xp = x * ap[u];
+            if (lr != 0.) red_add(t.bP + ch * t.bch + ip, x * lr);
+            if (k > i && xp * ar[u] != 0.) red_add(t.bL + ch * t.bch + ifl, xp * ar[u]);
+            if (l < j && xp * al[u] != 0.) red_add(t.bL + ch * t.bch + ifr, xp * al[u]);
+            eh.add(ch, sl, tsc * (xp * lr));
+          }
         }
       }
     }
