@@ -74,7 +74,8 @@ static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int nc
   auto take = [&](unsigned long long n) { unsigned long long r = o; o += (n + 1) & ~1ull; return r; };
   lay.aP = take(band); lay.aE = take(band); lay.aM = take(band); lay.a1 = take(band); lay.a2 = take(band);
   lay.aLl = take(band); lay.aLr = take(band); lay.aO = take(ext);
-  lay.bP = take(band * nch); lay.bEl = take(band * nch); lay.bEr = take(band * nch); lay.bM = take(band * nch);
+  // scatter mode never reads E by its right end (only the right-flank gather did): no second E table
+  lay.bP = take(band * nch); lay.bEl = take(band * nch); lay.bEr = take(LIN_SCATTER_ILOOP ? 0 : band * nch); lay.bM = take(band * nch);
   lay.bBl = take(band * nch); lay.bBr = take(band * nch); lay.b2 = take(band * nch); lay.bL = take(band * nch);
   lay.bO = take(ext * nch);
   lay.bch = band; lay.boch = ext;
