@@ -73,11 +73,12 @@ def test_scan_invariants_over_thousands_of_reads(gpu_lib):
         psi = r.psihat[k * L:(k + 1) * L]
         rss = r.rss[k * L:(k + 1) * L]
         inside = np.nonzero((psi != 0) & (psi != M - 1))[0]
-        if r.Ye[k] >= r.Ys[k]:
-            # the alignment is constrained to the posterior arg-max region: motif nodes exactly on [Ys, Ye]
-            assert inside.size > 0 and inside[0] == r.Ys[k] and inside[-1] == r.Ye[k], (k, r.Ys[k], r.Ye[k], inside[:3])
-            assert np.all(np.diff(psi[r.Ys[k]:r.Ye[k] + 1]) >= 0)       # the node chain is monotone
-            assert np.all(psi[:r.Ys[k]] == 0) and np.all(psi[r.Ye[k] + 1:] == M - 1)
+        if r.Ye[k] > r.Ys[k]:
+            # the alignment is constrained to the posterior arg-max region: motif nodes exactly on [Ys, Ye) -- position Ye
+            # is the first base emitted by the end node (the goldens of the reference show the same convention)
+            assert inside.size > 0 and inside[0] == r.Ys[k] and inside[-1] == r.Ye[k] - 1, (k, r.Ys[k], r.Ye[k], inside[:3])
+            assert np.all(np.diff(psi[r.Ys[k]:r.Ye[k]]) >= 0)           # the node chain is monotone
+            assert np.all(psi[:r.Ys[k]] == 0) and np.all(psi[r.Ye[k]:] == M - 1)
         assert set(rss) <= set("OLRHIBM")
         assert rss.count("L") == rss.count("R")                          # every opening base has its partner
 
