@@ -578,11 +578,28 @@ struct WarpLin {
   unsigned long long* bar;   // its mbarrier
   unsigned phase;            // parity of the next completion
 };
+// longest list the OUTSIDE phases index their per-entry sums with: in scatter mode the quads (by far the longest list
+// of a large automaton: 1 820 against 455 splits at S = 91) are walked without per-entry sums, so their count does not
+// size the per-warp shared memory any more (184 KB -> 88 KB per CTA at S = 91: two CTAs per SM instead of one)
+RHD int lin_outside_nmax(const LinHMM& h) {
+#if LIN_SCATTER_ILOOP
+  int m = h.S;
+  if (h.n_right > m) m = h.n_right;
+  if (h.n_left > m) m = h.n_left;
+  if (h.n_pair > m) m = h.n_pair;
+  if (h.n_split > m) m = h.n_split;
+  return m;
+#else
+  return h.n_max;
+#endif
+}
 // inside = true: only what the inside pass needs (no outside staging, no counts)
 // staged = true: room for the bulk-copy staging buffer of the split gather (inside B only)
+// n_max: longest list an outside / inside phase keeps per-entry sums for (lin_outside_nmax for the outside phases)
 RHD int warp_lin_bytes(int S, int Wmax, int nch, int n_max, int n_right, int n_left, bool inside, bool staged = false) {
+  // scatter mode keeps no energy-weighted per-entry sums (partT: only the enclosing-loop gather of outside P used them)
   int n = inside ? (S + n_max + 3 * LIN_CAP) * 8
-                 : (S + nch * S + 2 * nch * n_max + 3 * LIN_CAP + nch * 5 * (n_right + n_left)) * 8;
+                 : (S + nch * S + (LIN_SCATTER_ILOOP ? 1 : 2) * nch * n_max + 3 * LIN_CAP + nch * 5 * (n_right + n_left)) * 8;
   n += (2 * LIN_CAP + Wmax + 4) * 4;
   n = (n + 15) & ~15;
 #if LIN_SPLIT_TMA
@@ -599,7 +616,7 @@ RDEV WarpLin warp_lin_carve(unsigned char* base, int S, int Wmax, int nch, int n
   w.curA = p; p += S;
   w.curB = p; p += inside ? 0 : nch * S;
   w.partA = p; p += inside ? n_max : nch * n_max;
-  w.partT = p; p += inside ? 0 : nch * n_max;
+  w.partT = p; p += (inside || LIN_SCATTER_ILOOP) ? 0 : nch * n_max;
   w.bt = p; p += LIN_CAP;
   w.bf0 = p; p += LIN_CAP;
   w.bf1 = p; p += LIN_CAP;

@@ -100,7 +100,7 @@ static LinLayout make_lin_layout(int Lmax, int max_span, const LinHMM& h, int nc
   lay.sm_warp = b;
   lay.warp_bytes_in = warp_lin_bytes(h.S, Wmax, 1, h.n_max, 0, 0, true);
   lay.warp_bytes_inb = warp_lin_bytes(h.S, Wmax, 1, h.n_max, 0, 0, true, true);   // inside B: + staging of the split gather
-  lay.warp_bytes_out = warp_lin_bytes(h.S, Wmax, nch, h.n_max, h.n_right, h.n_left, false);
+  lay.warp_bytes_out = warp_lin_bytes(h.S, Wmax, nch, lin_outside_nmax(h), h.n_right, h.n_left, false);
   return lay;
 }
 
@@ -387,7 +387,7 @@ relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
     return;
   }
   if (PH >= PH_OUT_EM) {
-    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + w0 * lay.warp_bytes_out, q.S, lay.Wmax, NCH, h.n_max, h.n_right,
+    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + w0 * lay.warp_bytes_out, q.S, lay.Wmax, NCH, lin_outside_nmax(h), h.n_right,
                                h.n_left, false);
     w.pcnt = slot + lay.cnt + 5 * (h.n_right + h.n_left);
     w.pstride = (unsigned)lay.ncnt;
@@ -548,7 +548,7 @@ template <int WHICH, int NCH, int MODE = 0> LIN_KERNEL(32, 16) relem_lin_ext_ker
     return;
   }
   if (WHICH == 3) {
-    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp, S, lay.Wmax, NCH, h.n_max, h.n_right, h.n_left, false);
+    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp, S, lay.Wmax, NCH, lin_outside_nmax(h), h.n_right, h.n_left, false);
     w.pcnt = slot + lay.cnt + 5 * (h.n_right + h.n_left);
     w.pstride = (unsigned)lay.ncnt;
     for (int tt = lane_id(); tt < NCH * 5 * h.n_right; tt += WARP_N) w.cntR[tt] = 0.;
