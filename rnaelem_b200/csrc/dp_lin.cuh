@@ -1070,24 +1070,6 @@ RDEV void lin_in_E(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpL
   w_sync();
 }
 
-// one diagonal of the inside pass: the warp's cells (static interleaved assignment), phase by phase
-RDEV void lin_inside_diag(const LinCtx& c, const CTabs& t, int d, WarpLin& w) {
-  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
-  const int ncell = q.L + 1 - d, w0 = warp_id(), nw = n_warps();
-  for (int i = w0; i < ncell; i += nw) lin_in_L(c, t, i, d, w);
-  if (d >= q.min_pair) {
-    for (int i = w0; i < ncell; i += nw)
-      if (ok_P(q, i, d)) lin_in_P(c, t, i, d, w);
-    for (int i = w0; i < ncell; i += nw) {
-      bool gB = ok_B(q, i, d), gM = ok_M(q, i, d);
-      if (gB || gM) lin_in_B(c, t, i, d, ok_P(q, i, d), gB, gM, w);
-    }
-  }
-  if (d >= 3)
-    for (int i = w0; i < ncell; i += nw)
-      if (ok_E(q, i, d)) lin_in_E(c, t, i, d, ok_M(q, i, d), w);
-}
-
 // exterior row, one warp: O(j,s) <- O(i,(s.l,h)) P(i,j,(h,s.r)) ext | O(j-1,s1) emitR
 RDEV void lin_inside_ext(const LinCtx& c, const CTabs& t, WarpLin& w) {
   const LinHMM& h = LC.h;
@@ -1872,24 +1854,6 @@ RDEV void lin_out_ES(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w, 
   });
 }
 
-
-// one diagonal of the outside pass, phase-major over the warp's cells
-template <int NCH> RDEV void lin_outside_diag(const LinCtx& c, const CTabs& t, int d, WarpLin& w, EhAcc<NCH>& eh) {
-  const SeqView q = c.q;  // private copy: the shared-memory original would be re-read after every shared store
-  const int ncell = q.L + 1 - d, w0 = warp_id(), nw = n_warps();
-  if (d >= 3)
-    for (int i = w0; i < ncell; i += nw) {
-      bool gE = ok_E(q, i, d), gM = ok_M(q, i, d);
-      if (gE || gM) lin_out_EM<NCH>(c, t, i, d, gE, gM, w, eh);
-    }
-  if (d >= q.min_pair) {
-    for (int i = w0; i < ncell; i += nw)
-      if (ok_B(q, i, d)) lin_out_B<NCH>(c, t, i, d, ok_M(q, i, d), w);
-    for (int i = w0; i < ncell; i += nw)
-      if (ok_P(q, i, d)) lin_out_P<NCH>(c, t, i, d, ok_B(q, i, d), w, eh);
-  }
-  for (int i = w0; i < ncell; i += nw) lin_out_L<NCH>(c, t, i, d, d >= 3 && ok_E(q, i, d), w, eh);
-}
 
 }  // namespace lin
 }  // namespace relem

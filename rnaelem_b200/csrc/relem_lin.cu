@@ -298,6 +298,12 @@ template <int NCH> RDEV void lin_flush_counts(const LinLayout& lay, double* slot
 #ifndef LIN_MINB_SMALL
 #define LIN_MINB_SMALL 7
 #endif
+#ifndef LIN_FUSE_CELLS
+// chunk size (sequences x longest length) up to which the phases of a diagonal are fused into one launch.  Measured
+// (tools/minibatch_probe.py, 200-nt reads, two lanes): 64 sequence-evaluations 18.4 -> 16.3 ms fused, 128: 25.4 -> 26.7,
+// 512: 68 -> 99 (a warp that owns a heavy cell now carries all of its phases), so only chunks of <= ~40 reads fuse.
+#define LIN_FUSE_CELLS 8192
+#endif
 #ifndef LIN_STRIDED_SPARSE
 #define LIN_STRIDED_SPARSE 1   // A/B switch: cells of the sparse phases interleaved over the CTAs of a sequence
 #endif
@@ -411,6 +417,72 @@ relem_lin_phase_kernel(LinKArgs a LIN_SMEM_ARG) {
     }
     if (PH != PH_OUT_LF && PH != PH_OUT_LR) lin_flush_counts<NCH>(lay, slot, w, eh);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ fused diagonal
+// A training minibatch (~128 sequences) cannot fill 1036 resident CTAs phase by phase: each of the ~9 launches per
+// diagonal is a fraction of a wave and ends on its slowest cell.  For small chunks one launch per diagonal and direction
+// runs every phase of a cell in the warp that owns it (the phases of one cell depend only on each other and on other
+// diagonals), cells interleaved over the CTAs.  DIR 0 = inside (L, P, B, E), DIR 1 = outside (E/M, interior-loop
+// scatter, B, P, L).  Trainer only (no scan windows).
+template <int DIR, int NCH>
+LIN_KERNEL(LIN_THREADS, 7)
+relem_lin_diag_kernel(LinKArgs a LIN_SMEM_ARG) {
+#ifndef RELEM_HOST_EMU
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
+  const LinLayout& lay = a.lay;
+  const int blk = LIN_BLOCK_IDX;
+  const int sk = blk / a.ntile, tk = blk - sk * a.ntile;
+  if (sk >= a.count) return;
+  double* slot = a.scratch + (unsigned long long)sk * lay.stride;
+  if (slot[lay.hdr + 3] != 0.) return;
+  int n;
+  LinCtx& c = lin_attach(a, smem_raw, sk, slot, n);
+  const SeqView& q = c.q;
+  const int d = a.d;
+  if (d > q.W) return;
+  const int ncell = q.L + 1 - d;
+  const int w0 = warp_id(), nw = n_warps();
+  if (tk * nw >= ncell) return;
+  const int first = tk * nw + w0, step = a.ntile * nw;
+  CTabs t = lin_tabs(lay, slot);
+  const LinHMM& h = LC.h;
+  if (DIR == 0) {
+    const int wb = lay.warp_bytes_in > lay.warp_bytes_inb ? lay.warp_bytes_in : lay.warp_bytes_inb;
+    WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + w0 * wb, q.S, lay.Wmax, 1, h.n_max, 0, 0, true, false);
+    for (int i = first; i < ncell; i += step) {
+      lin_in_L(c, t, i, d, w);
+      if (d >= 5) {
+        const bool gP = ok_P(q, i, d), gB = ok_B(q, i, d), gM = ok_M(q, i, d);
+        if (gP) lin_in_P(c, t, i, d, w);
+        if (gB || gM) lin_in_B(c, t, i, d, gP, gB, gM, w);
+      }
+      if (d >= 3 && ok_E(q, i, d)) lin_in_E(c, t, i, d, ok_M(q, i, d), w);
+    }
+    return;
+  }
+  WarpLin w = warp_lin_carve(smem_raw + lay.sm_warp + w0 * lay.warp_bytes_out, q.S, lay.Wmax, NCH, lin_outside_nmax(h), h.n_right,
+                             h.n_left, false);
+  w.pcnt = slot + lay.cnt + 5 * (h.n_right + h.n_left);
+  w.pstride = (unsigned)lay.ncnt;
+  for (int tt = lane_id(); tt < NCH * 5 * h.n_right; tt += WARP_N) w.cntR[tt] = 0.;
+  for (int tt = lane_id(); tt < NCH * 5 * h.n_left; tt += WARP_N) w.cntL[tt] = 0.;
+  w_sync();
+  EhAcc<NCH> eh;
+  for (int k = 0; k < NCH * 2; ++k) eh.v[k] = 0.;
+  for (int i = first; i < ncell; i += step) {
+    const bool gE = d >= 3 && ok_E(q, i, d), gM = d >= 3 && ok_M(q, i, d);
+    if (gE || gM) lin_out_EM<NCH, 0>(c, t, i, d, gE, gM, w, eh);
+    if (gE) lin_out_ES<NCH, 0>(c, t, i, d, w, eh);
+    if (d >= 5) {
+      const bool gB = ok_B(q, i, d);
+      if (gB) lin_out_B<NCH, 0>(c, t, i, d, gM, w);
+      if (ok_P(q, i, d)) lin_out_P<NCH, 0, 1>(c, t, i, d, gB, w, eh);
+    }
+    lin_out_L<NCH, 0, 1>(c, t, i, d, gE, w, eh);
+  }
+  lin_flush_counts<NCH>(lay, slot, w, eh);
 }
 
 // ------------------------------------------------------------------------------------------------ zero
@@ -777,6 +849,7 @@ struct Runner {
   int resident_ctas = 148 * 7;
   int cmax = 30;                   // longest unpaired flank of an interior loop: min(30, max_iloop, W - 7)
   int fill = 4;                    // CTAs per resident slot a small launch aims for (RELEM_FILL)
+  bool fuse = false;               // chunk small enough for one launch per diagonal (RELEM_FUSE_SEQS)
   int tile_p = 128, tile_e = 256;   // cells per CTA of the phases that touch few cells
   int tile_k0 = 32, tile_d = 64;   // cells per CTA of the dense phases (measured sweet spot, RELEM_TILE_*)
   int tile_f = 64, tile_q = 256;   // flank kernels of outside L, interior-loop kernel of outside P
@@ -860,6 +933,18 @@ template <int PH, int MODE> static void launch_phase3(Runner& r, int d, int tile
   r.mark(PH);
 }
 
+// small chunks: every phase of one diagonal and direction in one launch (relem_lin_diag_kernel)
+template <int DIR, int NCH> static void launch_diag(Runner& r, int d) {
+  const int ncell_max = r.a.lay.Lmax + 1 - d;
+  if (ncell_max <= 0) return;
+  int tile = fit_tile(r, r.tile_d < ncell_max ? r.tile_d : ncell_max, ncell_max);
+  r.a.d = d; r.a.tile = tile; r.a.ntile = (ncell_max + tile - 1) / tile; r.a.win = 0;
+  r.mark(DIR ? 15 : 14);
+  LIN_LAUNCH(r, (relem_lin_diag_kernel<DIR, NCH>), r.a.count * r.a.ntile, LIN_THREADS,
+             DIR ? r.smem_out : (r.smem_in > r.smem_inb ? r.smem_in : r.smem_inb));
+  r.mark(DIR ? 15 : 14);
+}
+
 // scatter mode: zero b^P and the flank part of b^L of every slot of the chunk before its outside pass
 template <int NCH> static void launch_zero(Runner& r) {
 #if LIN_SCATTER_ILOOP
@@ -884,7 +969,9 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
     for (int d = W; d >= 3; --d) launch_phase<PH_K0_OUT, 1>(r, d, r.tile_k0, r.smem_k0);
     LIN_LAUNCH(r, relem_lin_filter_kernel, cnt, LIN_THREADS, r.smem_small);
   }
+  const bool fuse = LIN_SCATTER_ILOOP && r.fuse;
   for (int d = 0; d <= W; ++d) {
+    if (fuse) { launch_diag<0, NCH>(r, d); continue; }
     launch_phase<PH_IN_L, 1>(r, d, r.tile_d, r.smem_in);
     if (d >= 5) {
       launch_phase<PH_IN_P, 1>(r, d, r.tile_p, r.smem_in);
@@ -896,6 +983,7 @@ template <int NCH> static void run_chunk(Runner& r, bool filter, int NT) {
   launch_zero<NCH>(r);
   LIN_LAUNCH(r, (relem_lin_ext_kernel<3, NCH>), cnt, 32, r.smem_ext_out);
   for (int d = W; d >= 0; --d) {
+    if (fuse) { launch_diag<1, NCH>(r, d); continue; }
     if (d >= 3) launch_phase<PH_OUT_EM, NCH>(r, d, r.tile_p, r.smem_out);
 #if LIN_SCATTER_ILOOP
     if (d >= 3) launch_phase<PH_OUT_ES, NCH>(r, d, r.tile_q, r.smem_out);
@@ -1050,12 +1138,13 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
   st->k0pow = std::malloc(kp.size() * 8);
   std::memcpy(st->k0pow, kp.data(), kp.size() * 8);
   a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
-  r.smem.assign(std::max(std::max(r.smem_out, r.smem_inb), NT * in.nch * 8 + 16) + 64, 0);
+  r.smem.assign(std::max(std::max(r.smem_out, std::max(r.smem_in, r.smem_inb)), NT * in.nch * 8 + 16) + 64, 0);
   LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
   for (int k = 0; k < nseq; k += emu_chunk) {
     // poison: the gather passes must never read an entry they did not write
     { double* p = (double*)st->scratch; for (size_t z = 0; z < per * emu_chunk / 8; ++z) p[z] = std::nan(""); }
     a.base = k; a.count = std::min(emu_chunk, nseq - k);
+    if (const char* e = std::getenv("RELEM_FUSE_CELLS")) r.fuse = (long long)a.count * a.lay.Lmax <= std::atoll(e);
     if (in.nch == 2) run_chunk<2>(r, in.en.filter != 0, NT);
     else run_chunk<1>(r, in.en.filter != 0, NT);
   }
@@ -1122,12 +1211,16 @@ int lin_estep_launch(LinState* st, const LinLaunch& in, float* kernel_ms, int* l
       cudaStreamWaitEvent(st->lane[k], e0, 0);
     }
   }
+  // chunks of at most this many sequence positions run one fused launch per diagonal (see relem_lin_diag_kernel)
+  long long fuse_cells = LIN_FUSE_CELLS;
+  if (const char* e = std::getenv("RELEM_FUSE_CELLS")) fuse_cells = std::atoll(e);
   int chunk = 0;
   for (int base = 0; base < nseq; base += (int)nslots, ++chunk) {
     const int ln = chunk % nlanes;
     r.stream = nlanes >= 2 ? st->lane[ln] : main_stream;
     a.scratch = (double*)st->scratch + (size_t)ln * (size_t)nslots * lay.stride;
     a.base = base; a.count = std::min<int>((int)nslots, nseq - base);
+    r.fuse = (long long)a.count * lay.Lmax <= fuse_cells;
     if (in.nch == 2) run_chunk<2>(r, in.en.filter != 0, NT);
     else run_chunk<1>(r, in.en.filter != 0, NT);
   }
@@ -1166,7 +1259,9 @@ int lin_phase_timing(const LinState* st, const char** names, float* ms, int* lau
       "relem_lin_phase_kernel<8> outside P (2<-P, stack, exterior)", "relem_lin_phase_kernel<9> outside L (hairpin, parent)",
       "relem_lin_phase_kernel<10> outside L left flanks", "relem_lin_phase_kernel<11> outside L right flanks",
       "relem_lin_phase_kernel<12> outside P enclosing interior loops",
-      "relem_lin_phase_kernel<13> outside E interior loops (scatter to P and flanks)", "", ""};
+      "relem_lin_phase_kernel<13> outside E interior loops (scatter to P and flanks)",
+      "relem_lin_diag_kernel<0> inside, all phases of a diagonal (small chunks)",
+      "relem_lin_diag_kernel<1> outside, all phases of a diagonal (small chunks)"};
   int n = 0;
   if (!st) return 0;
   for (int k = 0; k < LIN_NPHASE_SLOTS && n < cap; ++k) {

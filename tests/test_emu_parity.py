@@ -17,6 +17,16 @@ def test_estep_emulated(name, emu_lib):
     caselib.check_estep(case, ctx)
 
 
+@pytest.mark.parametrize("name", ["m1", "ragged"])
+def test_estep_emulated_fused_diagonals(name, emu_lib, monkeypatch):
+    """small chunks take one launch per diagonal and direction (relem_lin_diag_kernel); the emulation takes that path
+    when RELEM_FUSE_CELLS says so"""
+    monkeypatch.setenv("RELEM_FUSE_CELLS", "1000000")
+    case = caselib.load_case(name)
+    ctx = caselib.make_ctx(case, lib=emu_lib)
+    caselib.check_estep(case, ctx)
+
+
 @pytest.mark.parametrize("name", SMALL)
 def test_scan_emulated(name, emu_lib):
     case = caselib.load_case(name)

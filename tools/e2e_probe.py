@@ -6,7 +6,7 @@ ctx = rb.Context(0)
 ctx.set_energy("~T2004~", 50, 30, 1e-4, 0); ctx.set_pattern("((.*.))")
 theta, lam, tau = bench.uniform_model(); ctx.set_params(theta, lam, tau)
 npos = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
-pos, neg = bench.make_dataset(npos, 1000)
+pos, neg = bench.make_dataset(npos, 1000, 200)
 seq_cat, off, ws, kind, gate = bench.pack(pos, neg)
 batch = ctx.batch(seq_cat, off, ws, kind, gate)
 for k in range(3):
