@@ -530,7 +530,7 @@ def main_own(args):
             value = world * m["step_cells"] * args.steps / m["dt"]
             e2e = world * m["step_cells"] * args.steps / m["dt_e2e"]
             roof = roofline_block(m["step_bytes"], m["kernel_ms"],
-                                  "E-step wavefront: relem_lin_phase_kernel<0..12> + exterior-row, prep, filter, fold kernels")
+                                  "E-step wavefront: relem_lin_phase_kernel<0..9,13> + exterior-row, prep, filter, fold kernels")
             roof["top_kernel"] = m["top"]
             prof, src = static_profile()
             issue = fp64 = None
