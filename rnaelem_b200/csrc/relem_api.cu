@@ -920,6 +920,9 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
       return 0;
 #else
       cudaStream_t st = (cudaStream_t)cv.stream;
+      // chunks alternate between two streams; the Viterbi launches share one value table and one work counter, so each
+      // waits for the one before it
+      if (!v.ev.empty()) cudaStreamWaitEvent(st, v.ev.back(), 0);
       if (cudaMemsetAsync(c->d_queue.p, 0, sizeof(int), st) != cudaSuccess) return 1;
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -1331,10 +1331,15 @@ int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_ch
   long long by_mem = (long long)(((double)(free_b + st->scratch_bytes) * 0.70) / (double)per);
   if (in.max_slots > 0) by_mem = std::min<long long>(by_mem, in.max_slots);
   if (by_mem < 1) { err = "not enough device memory for one sequence slot"; return 3; }
-  long long nslots = std::min<long long>(nseq, by_mem);
-  const long long have = (long long)(st->scratch_bytes / per);
+  // two lanes as in lin_estep_launch: while one lane's Viterbi kernel (few, fat CTAs) runs, the other lane's phase
+  // kernels fill the SMs.  The Viterbi launches themselves are serialised by the caller (they share one value table).
+  int nlanes = (nseq >= 64 && by_mem >= 2) ? 2 : 1;
+  if (const char* e = std::getenv("RELEM_SCAN_LANES")) nlanes = std::max(1, std::min(4, std::atoi(e)));
+  if (nlanes > by_mem) nlanes = (int)by_mem;
+  long long nslots = std::max<long long>(1, std::min<long long>((nseq + nlanes - 1) / nlanes, by_mem / nlanes));
+  const long long have = (long long)(st->scratch_bytes / ((size_t)nlanes * per));
   if (have >= 1 && have < nslots && have * 10 >= nslots * 8) nslots = have;
-  size_t need = (size_t)nslots * per;
+  size_t need = (size_t)nslots * nlanes * per;
   if (need > st->scratch_bytes) {
     if (st->scratch) cudaFree(st->scratch);
     st->scratch = nullptr; st->scratch_bytes = 0;
@@ -1355,14 +1360,33 @@ int lin_scan_launch(LinState* st, const LinScanLaunch& in, lin_chunk_fn after_ch
   a.scratch = (double*)st->scratch; a.k0pow = (const double*)st->k0pow; a.kp_n = KP;
   if (!st->ev0) { cudaEventCreate(&st->ev0); cudaEventCreate(&st->ev1); }
   cudaEvent_t e0 = st->ev0, e1 = st->ev1;   // owned by the state: nothing to release on the error returns below
-  cudaEventRecord(e0, r.stream);
+  cudaStream_t main_stream = r.stream;
   LIN_LAUNCH(r, relem_lin_gtab_kernel, 1, LIN_THREADS, 0);
-  for (int base = 0; base < nseq; base += (int)nslots) {
+  cudaEventRecord(e0, main_stream);
+  if (nlanes >= 2) {
+    for (int k = 0; k < nlanes; ++k) {
+      if (!st->lane[k]) cudaStreamCreateWithFlags(&st->lane[k], cudaStreamNonBlocking);
+      if (!st->lane_done[k]) cudaEventCreateWithFlags(&st->lane_done[k], cudaEventDisableTiming);
+      cudaStreamWaitEvent(st->lane[k], e0, 0);
+    }
+  }
+  int chunk = 0;
+  for (int base = 0; base < nseq; base += (int)nslots, ++chunk) {
+    const int ln = chunk % nlanes;
+    r.stream = nlanes >= 2 ? st->lane[ln] : main_stream;
+    a.scratch = (double*)st->scratch + (size_t)ln * (size_t)nslots * lay.stride;
     a.base = base; a.count = std::min<int>((int)nslots, nseq - base);
     run_chunk_scan(r, in.en.filter != 0, NT);
     cv.base = a.base; cv.count = a.count; cv.scratch = a.scratch; cv.stream = (void*)r.stream;
     if (after_chunk && after_chunk(user, cv)) { err = "Viterbi launch failed"; return 2; }
   }
+  if (nlanes >= 2) {
+    for (int k = 0; k < nlanes; ++k) {
+      cudaEventRecord(st->lane_done[k], st->lane[k]);
+      cudaStreamWaitEvent(main_stream, st->lane_done[k], 0);
+    }
+  }
+  r.stream = main_stream;
   e = cudaGetLastError();
   cudaEventRecord(e1, r.stream);
   if (e != cudaSuccess) { err = std::string("linear-space kernel launch: ") + cudaGetErrorString(e); return 2; }
