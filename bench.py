@@ -562,6 +562,7 @@ def main_own(args):
                     "device_passes": DEVICE_PASSES,
                     "device_cells_per_s": value * DEVICE_PASSES / PASSES,
                     "seq_evals_per_s": world * m["evals"] * args.steps / m["dt"],
+                    "state_cells_per_s": value * 7 * wl["S"],   # cells x 7 state types x S automaton states
                     "e2e": {"value": e2e, "unit": wl["unit"], "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
                             "ms_per_step": 1e3 * m["dt_e2e"] / args.steps, "kernel_ms_per_step": m["e2e_kernel_ms"]},
                     "gpu_launches": m["launches"], "clocks": m["clocks"], "roofline": roof, "issue": issue, "fp64": fp64}
