@@ -1015,12 +1015,14 @@ int relem_scan_run(relem_ctx* c, relem_batch* b, relem_scan_out* out) {
 
 int relem_scan(relem_ctx* c, int nseq, const uint8_t* seq_cat, const int64_t* off, const double* ws_cat,
                relem_scan_out* out) {
-  relem_batch* b = nullptr;
-  int rc = relem_batch_create(c, nseq, seq_cat, off, ws_cat, nullptr, nullptr, &b);
+  if (!c) return RELEM_EINVAL;
+  if (!bind_device(c)) return fail(c, RELEM_ECUDA, "cudaSetDevice failed");
+  // same staging batch as relem_estep: device buffers that only grow.  Allocating and freeing six buffers per call next
+  // to a ~100 GB scratch allocation cost 0.15-0.5 s per call (tools/scan_e2e_probe.py).
+  if (!c->staging) c->staging = new relem_batch();
+  int rc = batch_fill(c, c->staging, nseq, seq_cat, off, ws_cat, nullptr, nullptr);
   if (rc) return rc;
-  rc = relem_scan_run(c, b, out);
-  relem_batch_destroy(c, b);
-  return rc;
+  return relem_scan_run(c, c->staging, out);
 }
 
 void relem_assigned_range(int64_t total, int n, int k, int64_t* from, int64_t* to) {
