@@ -158,12 +158,15 @@ def scan_inputs(case):
     return seqs, wss
 
 
-def check_scan(case, ctx):
+def check_scan(case, ctx, host_buffers=False):
     seqs, wss = scan_inputs(case)
     sc, off, wc = rb.pack_batch(seqs, wss)
-    b = ctx.batch(sc, off, wc)
-    r = ctx.scan_run(b)
-    b.close()
+    if host_buffers:   # relem_scan: host buffers in, the context's staging batch underneath
+        r = ctx.scan(sc, off, wc)
+    else:
+        b = ctx.batch(sc, off, wc)
+        r = ctx.scan_run(b)
+        b.close()
     gold = case["scan"]
     assert len(gold["records"]) == len(seqs)
     M = ctx.M

@@ -34,6 +34,19 @@ def test_scan_emulated(name, emu_lib):
     caselib.check_scan(case, ctx)
 
 
+def test_host_buffer_calls_reuse_the_staging_batch(emu_lib):
+    """relem_scan / relem_estep keep one staging batch per context whose device buffers only grow: calls with a larger,
+    then a smaller, then a different-model batch must each see their own data"""
+    big, small = caselib.load_case("ragged"), caselib.load_case("m0")
+    ctx = caselib.make_ctx(big, lib=emu_lib)
+    caselib.check_scan(big, ctx, host_buffers=True)
+    caselib.check_estep(big, ctx, via_host_call=True)
+    ctx2 = caselib.make_ctx(small, lib=emu_lib)
+    caselib.check_scan(small, ctx2, host_buffers=True)
+    caselib.check_scan(small, ctx2, host_buffers=True)
+    caselib.check_scan(big, ctx, host_buffers=True)
+
+
 @pytest.mark.parametrize("name", ["m0", "ragged"])
 def test_exterior_row_rescaling(name, emu_renorm_lib):
     """exterior rows are mantissa + power-of-two exponent per position; with the thresholds at 0.5 / 2 every column is
