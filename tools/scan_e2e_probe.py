@@ -1,5 +1,6 @@
+"""host-buffer scan (relem_scan) against the resident form: where the time of a call goes (batch upload, kernels, release)"""
 import os, sys, time, tempfile
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench, rnaelem_b200 as rb
 from rnaelem_b200 import hostio
