@@ -51,6 +51,12 @@ def test_cli_emulated(name, emu_cli, tmp_path):
     clilib.check_case(emu_cli, name, str(tmp_path))
 
 
+def test_scan_rounds_keep_input_order(emu_cli, tmp_path):
+    """the scanner works in rounds of RELEM_SCAN_CHUNK reads per GPU, formatted one round behind on host threads:
+    rounds of 3 reads must print the same records, in input order, and the same E[N]"""
+    clilib.check_case(emu_cli, "ragged_scan", str(tmp_path), extra_env={"RELEM_SCAN_CHUNK": "3"})
+
+
 def test_unknown_option_and_subcommand(product_cli):
     p = subprocess.run([product_cli, "--no-such-flag"], capture_output=True, text=True)
     assert p.returncode == 1
