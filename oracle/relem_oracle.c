@@ -153,6 +153,9 @@ static void load_energy(orc_model* m, int which) { /* which sub-block each secti
     for (int k = 0; k < 25; ++k) m->int11[a + 1][b + 1][k / 5][k % 5] = lw(e->i11[(a * 7 + b) * 25 + k], 0);
     for (int k = 0; k < 125; ++k) m->int21[a + 1][b + 1][k / 25][(k / 5) % 5][k % 5] = lw(e->i21[(a * 7 + b) * 125 + k], 0);
   }
+  /* energy_param.hpp:597-598 clears only the first 8000 entries of int22; the rest, unless read from the file, is
+   * never written and holds +0.0 in the reference's binaries (tests/golden/tables_*.npz) */
+  for (int k = 8000; k < 40000; ++k) (&m->int22[0][0][0][0][0][0])[k] = 0.;
   for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) for (int k = 0; k < 256; ++k)
     m->int22[a + 1][b + 1][1 + k / 64][1 + (k / 16) % 4][1 + (k / 4) % 4][1 + k % 4] = lw(e->i22[(a * 6 + b) * 256 + k], 0);
   for (int d = 0; d <= 30; ++d) {

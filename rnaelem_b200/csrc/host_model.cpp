@@ -252,6 +252,14 @@ void EnergyTables::build(const EnergyInts& e) {
     for (int k = 0; k < 25; ++k) int11[a + 1][b + 1][k / 5][k % 5] = lw(e.int11[a][b][k]);
     for (int k = 0; k < 125; ++k) int21[a + 1][b + 1][k / 25][(k / 5) % 5][k % 5] = lw(e.int21[a][b][k]);
   }
+  // The reference clears only the first 8*8*5*5*5 = 8 000 of the 40 000 entries of int22 before it reads the file
+  // (energy_param.hpp:597-598); the entries with an unknown base ('N') beyond that are never written and read as
+  // +0.0 -- log-weight 0, i.e. no penalty -- in its binaries (fresh zero pages; tests/golden/tables_*.npz holds the
+  // dump).  Reads with N bases next to a 2x2 interior loop only agree with the reference if this is reproduced.
+  {
+    double* p22 = &int22[0][0][0][0][0][0];
+    for (int k = 8000; k < 40000; ++k) p22[k] = 0.;
+  }
   for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) for (int k = 0; k < 256; ++k)
     int22[a + 1][b + 1][1 + k / 64][1 + (k / 16) % 4][1 + (k / 4) % 4][1 + k % 4] = lw(e.int22[a][b][k]);
   for (int d = 0; d <= 30; ++d) {

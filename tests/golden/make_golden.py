@@ -342,12 +342,41 @@ def make_cases_round2():
     make_case("plstem", mp, fq, 1)
 
 
+def make_case_nbases():
+    """reads with unknown bases (code 0: cannot pair, emitted like any base), lower case and T for U
+    (bio_sequence.hpp:28-41)"""
+    tmp = os.path.join(HERE, "_tmp")
+    os.makedirs(tmp, exist_ok=True)
+    mp = os.path.join(tmp, "synth.model")
+    if not os.path.exists(mp):
+        open(mp, "w").write(SYNTH_MODEL % ("~T2004~", 50, "0.0001"))
+    fq = os.path.join(tmp, "nbases.fq")
+    rnd = random.Random(31)
+    with open(fq, "w") as f:
+        for k in range(4):
+            L = (90, 64, 120, 33)[k]
+            s = [rnd.choice("ACGU") for _ in range(L)]
+            for _ in range((6, 2, 15, 0)[k]):
+                s[rnd.randrange(0, L)] = rnd.choice("NnXR-")
+            for z in range(L):
+                if rnd.random() < 0.15:
+                    s[z] = {"A": "a", "C": "c", "G": "g", "U": rnd.choice("tTu")}.get(s[z], s[z])
+            if k == 3:
+                s[10:14] = list("NNNN")   # a run of unknown bases inside a short read
+            f.write("@nb%d\n%s\n+\n%s%s\n" % (k, "".join(s), "+" * L, "!" if k != 1 else "+"))
+    make_case("nbases", mp, fq, 1)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "round2":
         make_cases_round2()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "nbases":
+        make_case_nbases()
         sys.exit(0)
     make_tables()
     make_hmm()
     make_cases()
     make_bpp()
     make_cases_round2()
+    make_case_nbases()

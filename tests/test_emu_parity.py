@@ -7,7 +7,7 @@ import pytest
 import caselib
 import rnaelem_b200 as rb
 
-SMALL = ["m0", "m1", "m3", "ragged"]
+SMALL = ["m0", "m1", "m3", "ragged", "nbases"]
 
 
 @pytest.mark.parametrize("name", SMALL)
