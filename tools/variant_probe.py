@@ -29,8 +29,17 @@ VARIANTS = {
   "pat_dots": model(pattern=".."),
   "pat_nest": model(pattern="((..))"),
   "pat_star": model(pattern="(.*)*(.)"),
+  # entries of the shipped pattern_list (and a two-hairpin pattern), Andronescu2007 for some
+  "pl_a": model(pattern=".(.......)"),
+  "pl_b": model(pattern="(..(...)).", param="~A2007~"),
+  "pl_c": model(pattern="(...)*.....", lam=(0.5, 0.2)),
+  "pl_d": model(pattern="....(*...).", param="~A2007~", span=30),
+  "pl_e": model(pattern="((...*.)..)"),
+  "pl_f": model(pattern="..(.(*...))", span=40),
+  "two_hairpins": model(pattern="(...)(...)"),
+  "two_hairpins_gap": model(pattern="(..).*(..)", param="~A2007~"),
 }
-names = sys.argv[1:] or list(VARIANTS)
+names = [n for n in (sys.argv[1:] or list(VARIANTS)) if n in VARIANTS]
 fq = os.path.join(OUT, "probe.fq")
 mg.write_fq(fq, 3, 70, 77)
 for name in names:
@@ -38,6 +47,35 @@ for name in names:
     open(mp, "w").write(VARIANTS[name])
     try:
         mg.HERE = OUT   # case file goes to /tmp/probe
+        mg.make_case("probe_" + name, mp, fq, 1)
+        case = json.load(open(os.path.join(OUT, "case_probe_%s.json" % name)))
+        ctx = caselib.make_ctx(case, lib=conftest.EMU_LIB)
+        caselib.check_estep(case, ctx)
+        if "scan" in case: caselib.check_scan(case, ctx)
+        print("OK   ", name, flush=True)
+    except BaseException as e:
+        print("FAIL ", name, type(e).__name__, str(e)[:300].replace("\n", " | "), flush=True)
+
+# unusual reads with the default model (names prefixed "in_")
+READS = {
+    "in_homopolymer": ["A" * 60, "U" * 45],
+    "in_gc_stems": ["GGGGGGGGGGAAAACCCCCCCCCC" * 2, "GCGCGCGCGCGCGCGCGCGCGCGCGCGCGCGC"],
+    "in_len1_2": ["A", "GC", "ACG", "ACGU"],
+    "in_lenW": ["ACGUGCAUGCAGUCGAUCGAUGCAUGCUAGCUAGCAUGCAUCGAUGCAUGC", "ACGUGCAUGCAGUCGAUCGAUGCAUGCUAGCUAGCAUGCAUCGAUGCAUGCA",
+                "ACGUGCAUGCAGUCGAUCGAUGCAUGCUAGCUAGCAUGCAUCGAUGCAUG"],
+    "in_allN": ["N" * 30, "NNNNNACGUNNNNN"],
+}
+mp = os.path.join(OUT, "default.model")
+open(mp, "w").write(mg.SYNTH_MODEL % ("~T2004~", 50, "0.0001"))
+for name, seqs in READS.items():
+    if sys.argv[1:] and name not in sys.argv[1:]:
+        continue
+    fq = os.path.join(OUT, name + ".fq")
+    with open(fq, "w") as f:
+        for k, sq in enumerate(seqs):
+            f.write("@r%d\n%s\n+\n%s%s\n" % (k, sq, "+" * len(sq), "!" if k % 2 == 0 else "+"))
+    try:
+        mg.HERE = OUT
         mg.make_case("probe_" + name, mp, fq, 1)
         case = json.load(open(os.path.join(OUT, "case_probe_%s.json" % name)))
         ctx = caselib.make_ctx(case, lib=conftest.EMU_LIB)
