@@ -16,6 +16,10 @@ CASES = {
  "softmax_rhos": ["-f", T+"/trna.fq", "-m", "(.....)", "--theta-softmax", "--rho-s", "0.3", "--max-iter", "4", "--batch-size", "-1"],
  "epsilon": ["-f", T+"/ragged.fq", "-m", "(.*)", "--max-iter", "30", "--batch-size", "-1", "--epsilon", "0.05"],
  "nbases_cli": ["-f", T+"/nbases.fq", "-m", "((.*.))", "--max-iter", "3", "--batch-size", "-1"],
+ "batch_gt_n": ["-f", T+"/synth.fq", "-m", "((.*.))", "--max-iter", "4", "--batch-size", "10"],
+ "batch_1": ["-f", T+"/ragged.fq", "-m", "(.*)", "--max-iter", "9", "--batch-size", "1"],
+ "iter_0": ["-f", T+"/ragged.fq", "-m", "(.*)", "--max-iter", "0", "--batch-size", "-1"],
+ "two_stems_train": ["-f", T+"/plstem.fq", "-m", "(.(..*..).)", "--max-iter", "2", "--batch-size", "-1", "--energy-param", "~A2007~", "-w", "80"],
 }
 for name, args in CASES.items():
     if sys.argv[1:] and name not in sys.argv[1:]: continue
