@@ -231,12 +231,18 @@ template <class V> RDEV void enum_E(const ModelView& m, const SeqView& q, int i,
   int a0 = ld_ro(h.quad_off + s), a1 = ld_ro(h.quad_off + s + 1);
   if (a0 == a1) return;
   int C = q.C;
-  int lmin = j - C > i ? j - C : i;
+  // u1 <= C and u1 + u2 <= Cs.  Cs = C in the inside / Viterbi passes; the reference's outside pass does not bound u2
+  // (energy_model.hpp:529), only the energy function does (30): that matters when --max-internal-loop is the binding
+  // limit (see LinCtx::Csum in dp_lin.cuh)
+  int Cs = C;
+  if (V::kOutside && !m.en.no_ene && C < 30 && C < q.W - 7) Cs = 30;
+  int lmin = j - Cs > i ? j - Cs : i;
   if (q.bpr) {
     // same visiting order (l descending, k ascending), inner pairs found by scanning row l of the right-indexed pair
     // mask: bit dd <-> pair (l-dd, l), k ascending = dd descending
     for (int l = j; l >= lmin; --l) {
-      int kmax = i + C - (j - l);
+      int kmax = i + Cs - (j - l);
+      if (kmax > i + C) kmax = i + C;
       if (kmax > l) kmax = l;
       const unsigned* rl = q.bpr + l * q.mw;
       int dlo = l - kmax;
@@ -262,7 +268,8 @@ template <class V> RDEV void enum_E(const ModelView& m, const SeqView& q, int i,
     return;
   }
   for (int l = j; l >= lmin; --l) {
-    int kmax = i + C - (j - l);
+    int kmax = i + Cs - (j - l);
+    if (kmax > i + C) kmax = i + C;
     if (kmax > l) kmax = l;
     for (int k = i; k <= kmax; ++k) {
       if (k == i && l == j) continue;

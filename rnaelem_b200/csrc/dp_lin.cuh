@@ -102,6 +102,12 @@ struct LinCtx {
   const double* wsf;    // exp(position weight) [L]
   const double* k0pow;  // kappa0^u, u = 0..W+1
   int Ceff;             // min(C, 30): loops longer than 30 have zero weight (energy_param.hpp:754-755)
+  // The reference's OUTSIDE pass bounds the right flank of an interior loop by the loop variable itself
+  // (energy_model.hpp:529), i.e. only by the energy function: it visits u1 <= C, u1 + u2 <= 30 where its inside pass
+  // visits u1 + u2 <= C.  The sets differ only when --max-internal-loop is the binding limit (C < 30 and C < W - 7,
+  // energies on); Csum / Cfl are then 30 / min(30, W), otherwise both equal Ceff (see lin_outside_limits).
+  int Csum;             // bound on u1 + u2 in the outside pass
+  int Cfl;              // longest flank the outside pass can reach
   // scanner: motif start fixed at position ys (-1: unconstrained), InsideEndFun / OutsideEndFun,
   // motif_scanner.hpp:606-639,720-760; linear start / inner / end posteriors [L+1] each
   int ys;
@@ -479,7 +485,7 @@ RDEV void k0_outside_cell(const LinCtx& c, const K0Tabs& t, int i, int d, int* s
     bP += ldexp(t.O[i] * t.bO[j], (int)(t.eO[i] + t.fO[j])) * (ne ? 1. : nl_l_ext(&q, i, j - 1, 1));
     // enclosing pairs: this cell is the inner pair (k=i,l=j) of E(i',j')
     const int C = c.Ceff;
-    const int hi = W < d + C + 2 ? W : d + C + 2;
+    const int hi = W < d + c.Csum + 2 ? W : d + c.Csum + 2;
     double acc = 0., accg = 0.;
     for (int u10 = 0; u10 <= C; u10 += WARP_N) {
       int u1 = u10 + lane, i2 = i - u1, lo = d + u1 + 2;
@@ -695,11 +701,19 @@ template <class E> RDEV void batch_eval(WarpLin& w, int n, E energy) {
     w_sync();                                         \
   }
 
-// inner pairs (k,l) of E(i,j): u1 = k-i, u2 = j-l, u1+u2 <= C, not both 0 (energy_model.hpp:413-426)
-template <class F> RDEV void walk_inner(const LinCtx& c, int i, int d, WarpLin& w, F flush) {
+// outside-pass limits of a sequence with band W (see LinCtx::Csum)
+RDEV void lin_outside_limits(int W, int max_iloop, bool no_ene, int Ceff, int& Csum, int& Cfl) {
+  const bool binding = !no_ene && max_iloop < 30 && max_iloop < W - 7;
+  Csum = binding ? 30 : Ceff;
+  Cfl = binding ? (W < 30 ? W : 30) : Ceff;
+}
+
+// inner pairs (k,l) of E(i,j): u1 = k-i <= C, u2 = j-l, u1+u2 <= csum, not both 0 (energy_model.hpp:413-426; csum = C
+// in the inside pass, LinCtx::Csum in the outside pass)
+template <class F> RDEV void walk_inner(const LinCtx& c, int i, int d, WarpLin& w, int csum, F flush) {
   const SeqView& q = c.q;
   const int j = i + d, C = c.Ceff, lane = lane_id();
-  const int lo = d - C > 0 ? d - C : 0;
+  const int lo = d - csum > 0 ? d - csum : 0;
   auto energy = [&](int k, int l) { return nl_e_loop(&q, i - 1, j, k, l - 1); };
   int n = 0;
   for (int u10 = 0; u10 <= C; u10 += WARP_N) {
@@ -1033,7 +1047,7 @@ RDEV void lin_in_E(const LinCtx& c, const CTabs& t, int i, int d, bool gM, WarpL
   if (h.n_quad > 0) {
     const double* rL = t.aLl + cidx(q, i, 0);
     const double* rR = t.aLr + cidx(q, j, 0);
-    walk_inner(c, i, d, w, [&](int n) {
+    walk_inner(c, i, d, w, c.Ceff, [&](int n) {
       for (int a = lane; a < h.n_quad; a += WARP_N) {
         int s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a), s3 = ld_ro(h.q_s3 + a);
         const double* bf = ld_ro(h.slot + ld_ro(h.q_tgt + a)) ? w.bf1 : w.bf0;
@@ -1256,6 +1270,11 @@ RDEV void lin_out_EM(const LinCtx& c, const CTabs& t, int i, int d, bool gE, boo
       if (fl & 2) wt *= wsr;
       if ((i - 1 == c.ys && !(fl & LIN_F_START)) || (j == c.ys && !(fl & LIN_F_RSTART))) wt = 0.;
       double ac = t.aE[il + s1];
+      // the reference adds to an outside value only when the transition's posterior is non-zero
+      // (motif_trainer.hpp:372: `if (zeroL == z) return;` before the updates).  That only shows where its inside and
+      // outside passes enumerate different interior loops (LinCtx::Csum): a state of E with no inside derivation must
+      // not hand outside weight down to the extra loops.
+      if (ac == 0.) wt = 0.;
       for (int ch = 0; ch < NCH; ++ch) {
         double contrib = t.bP[ch * t.bch + pb + s] * wt;
         w.partA[ch * NM + pz] = contrib;
@@ -1783,7 +1802,7 @@ RDEV void lin_out_L(const LinCtx& c, const CTabs& t, int i, int d, bool gE, Warp
       for (int s = lane; s < S; s += WARP_N)
         for (int ch = 0; ch < NCH; ++ch) t.bL[ch * t.bch + il + s] += cL[ch * S + s];
   } else if (d >= 1) {
-    if (LIN_SCATTER_ILOOP && PART == 1 && d <= c.Ceff && h.n_quad > 0) {
+    if (LIN_SCATTER_ILOOP && PART == 1 && d <= c.Cfl && h.n_quad > 0) {
       // a possible flank: the loops it flanks have already added their share (lin_out_ES) to the zeroed entry
       for (int s = lane; s < S; s += WARP_N)
         for (int ch = 0; ch < NCH; ++ch) t.bL[ch * t.bch + il + s] += cL[ch * S + s];
@@ -1808,7 +1827,7 @@ RDEV void lin_out_ES(const LinCtx& c, const CTabs& t, int i, int d, WarpLin& w, 
   const unsigned r0 = cidx(q, i, 0);
   const double* rL = t.aLl + r0;
   const double* rR = t.aLr + cidx(q, j, 0);
-  walk_inner(c, i, d, w, [&](int n) {
+  walk_inner(c, i, d, w, c.Csum, [&](int n) {
     for (int a = lane; a < h.n_quad; a += WARP_N) {
       const int s = ld_ro(h.q_tgt + a), s1 = ld_ro(h.q_s1 + a), s2 = ld_ro(h.q_s2 + a), s3 = ld_ro(h.q_s3 + a);
       const int sl = ld_ro(h.slot + s);

@@ -29,6 +29,7 @@ RDEV double lse2(double x, double y) {
 
 // ------------------------------------------------------------------------------------------------ visitors
 template <class CON> struct SumV {
+  static constexpr bool kOutside = false;
   RDEV unsigned bidx(const SeqView& q, int plane, int i, int d, int s) const { return band_idx(q, plane, i, d, s); }
   const double* tab;
   const double* otab;
@@ -58,6 +59,7 @@ RDEV unsigned long long pack_trace(int tt, const Geo& g) {
 }
 #define RELEM_NO_TRACE 0xFFFFFFFFFFFFFFFFull
 template <class CON> struct MaxV {
+  static constexpr bool kOutside = false;
   RDEV unsigned bidx(const SeqView& q, int plane, int i, int d, int s) const { return band_idx(q, plane, i, d, s); }
   const double* tab;
   const double* otab;
@@ -111,6 +113,7 @@ RDEV int plane_of_same_cell(int tt) {
 }
 
 template <int NCH, int HOOK, class CON> struct ScatV {
+  static constexpr bool kOutside = true;   // enum_E: the reference's outside pass visits a larger loop set
   RDEV unsigned bidx(const SeqView& q, int plane, int i, int d, int s) const { return band_idx(q, plane, i, d, s); }
   const double* tab;
   const double* otab;

@@ -56,6 +56,7 @@ struct VitRegion {
 };
 
 template <class CON> struct VitBase {
+  static constexpr bool kOutside = false;
   const double* tab;
   const double* otab;
   CON con;

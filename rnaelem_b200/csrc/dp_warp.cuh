@@ -94,12 +94,15 @@ RDEV void clear_kbits(WarpSm&, int) {}
 
 // Interior-loop candidates of E(i,j): inner pairs (k,l) with u1+u2 <= C (energy_model.hpp:413-426).  The walker
 // fills the warp's batch buffer (k, l, loop energy) and calls `flush(n)` whenever it is full and at the end.
-template <class F> RDEV void walk_inner_pairs(const ModelView& m, const SeqView& q, int i, int d, WarpSm& w, F flush) {
+template <class F> RDEV void walk_inner_pairs(const ModelView& m, const SeqView& q, int i, int d, WarpSm& w, bool outside, F flush) {
   const int j = i + d, C = q.C, lane = lane_id();
   int n = 0;
-  int lmin = j - C > i ? j - C : i;
+  int Cs = C;   // bound on u1 + u2: see enum_E (dp_enum.cuh)
+  if (outside && !m.en.no_ene && C < 30 && C < q.W - 7) Cs = 30;
+  int lmin = j - Cs > i ? j - Cs : i;
   for (int l = j; l >= lmin; --l) {
-    int kmax = i + C - (j - l);
+    int kmax = i + Cs - (j - l);
+    if (kmax > i + C) kmax = i + C;
     if (kmax > l) kmax = l;
     for (int k0 = i; k0 <= kmax; k0 += WARP_N) {
       int k = k0 + lane;
@@ -294,7 +297,7 @@ RDEV void wc_inside_cell(const ModelView& m, const SeqView& q, double* tab, int 
   if (gE) {
     acc_clear(w);
     if (h.n_quad > 0) {
-      walk_inner_pairs(m, q, i, d, w, [&](int n) {
+      walk_inner_pairs(m, q, i, d, w, false, [&](int n) {
         for (int base = 0; base < h.n_quad; base += WARP_N) {
           int a = base + lane, key = -1;
           Lse v; v.init();
@@ -485,7 +488,7 @@ RDEV void wc_outside_cell(const ModelView& m, const SeqView& q, const double* ta
         for (int c = 0; c < NCH; ++c) { QC(PL_L, s, c) += p[c]; eh[c * 2 + slot] += tH * p[c]; }
     }
     if (h.n_quad > 0) {
-      walk_inner_pairs(m, q, i, d, w, [&](int n) {
+      walk_inner_pairs(m, q, i, d, w, true, [&](int n) {
         for (int base = 0; base < h.n_quad; base += WARP_N) {
           int a = base + lane;
           if (a >= h.n_quad) continue;

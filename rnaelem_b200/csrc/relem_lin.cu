@@ -175,6 +175,7 @@ RDEV LinCtx& lin_attach(const LinKArgs& a, unsigned char* smem_raw, int sk, doub
     q.ws = a.b.ws + o; q.emit0 = nullptr; q.emitT = nullptr;
     c.wsf = slot + lay.wsf; c.k0pow = a.k0pow;
     c.Ceff = C < 30 ? C : 30;
+    lin_outside_limits(W, LC.en.max_iloop, LC.en.no_ene != 0, c.Ceff, c.Csum, c.Cfl);
     c.ys = FROM_HDR ? (int)slot[lay.hdr + 6] : -1;
     c.pys = slot + lay.post; c.pyi = c.pys + (lay.Lmax + 2); c.pye = c.pyi + (lay.Lmax + 2);
   }
@@ -503,7 +504,8 @@ template <int NCH> LIN_KERNEL(LIN_THREADS, 8) relem_lin_zero_kernel(LinKArgs a L
   const int W = L < LC.en.max_span ? L : LC.en.max_span;
   const int S = LC.h.S, W1 = W + 1;
   const int C = W - 7 < LC.en.max_iloop ? W - 7 : LC.en.max_iloop;
-  const int Ceff = C < 30 ? C : 30;
+  int Ceff = C < 30 ? C : 30, csum_unused;
+  lin_outside_limits(W, LC.en.max_iloop, LC.en.no_ene != 0, Ceff, csum_unused, Ceff);   // flanks the scatter can reach
   // b^P: bch doubles per channel, even and 16-byte aligned (slot offsets are even, the scratch is 256-byte aligned)
   const unsigned long long nP = (unsigned long long)NCH * lay.bch / 2;
   double2* pP = reinterpret_cast<double2*>(slot + lay.bP);

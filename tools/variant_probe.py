@@ -16,6 +16,12 @@ def model(pattern="((.*.))", span=50, iloop=30, lam=(0.3, 0.6), tau=0.1, min_bpp
 VARIANTS = {
   "iloop8": model(iloop=8),
   "iloop0": model(iloop=0),
+  "iloop1": model(iloop=1),
+  "iloop2": model(iloop=2),
+  "iloop3": model(iloop=3),
+  "iloop20": model(iloop=20),
+  "iloop2_nofilter": model(iloop=2, min_bpp="0"),
+  "iloop2_span20": model(iloop=2, span=20),
   "iloop40": model(iloop=40),
   "span12": model(span=12),
   "span8": model(span=8),
